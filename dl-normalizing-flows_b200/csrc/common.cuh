@@ -1,0 +1,120 @@
+// Shared helpers for the RealNVP hot-path kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include "../../include/rnvp.h"
+
+namespace rnvp {
+
+constexpr float kBnEps = 1e-5f;       // nn.BatchNorm2d default; literal at modules_realnvp.py:289,301
+constexpr float kBnMomentum = 0.1f;   // nn.BatchNorm2d default
+constexpr int kNumSMs = 148;          // B200
+
+void set_error(const char* fmt, ...);
+
+#define RNVP_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::rnvp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return RNVP_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+#define RNVP_TRY(expr)                 \
+  do {                                 \
+    int _s = (expr);                   \
+    if (_s != RNVP_OK) return _s;      \
+  } while (0)
+
+#define RNVP_REQUIRE(cond, ...)                      \
+  do {                                               \
+    if (!(cond)) {                                   \
+      ::rnvp::set_error(__VA_ARGS__);                \
+      return RNVP_ERR_INVALID;                       \
+    }                                                \
+  } while (0)
+
+#define RNVP_LAUNCH_CHECK() RNVP_CUDA(cudaGetLastError())
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int pad_to(int a, int m) { return (a + m - 1) / m * m; }
+
+inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
+  int64_t g = ceil_div64(work_items, per_block);
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+// ---------------------------------------------------------------------------
+// geometry of one coupling as the elementwise kernels see it
+//   x is NHWC [B,S,S,C].  "in-branch" channels feed the s/t net through in_bn,
+//   "transformed" channels receive the affine map.
+//   checkerboard (modules_realnvp.py:264-302): both are all C channels; the
+//     in-branch sees x*m, the transform acts where (1-m) = 1, m = (cfg+i+j)&1.
+//   channelwise (modules_realnvp.py:324-370): cfg=1 -> on = first half,
+//     off = second half; cfg=0 the other way round; no spatial mask.
+// ---------------------------------------------------------------------------
+struct CplGeom {
+  int B, S, C;        // x tensor
+  int cio;            // channels transformed (= in-branch channels)
+  int on_off;         // first transformed channel
+  int in_off;         // first in-branch channel
+  int ckbd;           // 1 checkerboard, 0 channelwise
+  int cfg;            // mask configuration
+  int cin_pad;        // padded channel stride of h0 (s/t net input)
+  int cst_pad;        // padded channel stride of st (s/t net output, 2*cio real)
+  __host__ __device__ int P() const { return B * S * S; }
+  __host__ __device__ int cin() const { return ckbd ? 2 * cio + 1 : 2 * cio; }
+  // value of the reference's `mask` at pixel p (1 = passes to the s/t net)
+  __device__ float mask_in(int p) const {
+    if (!ckbd) return 1.f;
+    int j = p % S, i = (p / S) % S;
+    return (float)((cfg + i + j) & 1);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean / rstd / scale / shift of one BN channel from (sum, sumsq) over `count` values
+struct BnCoef { float mean, rstd, scale, shift, var; };
+__device__ __forceinline__ BnCoef bn_coef_from_sums(double s, double ss, double count, float gamma, float beta) {
+  double mean = s / count;
+  double var = ss / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  BnCoef c;
+  c.mean = (float)mean;
+  c.var = (float)var;
+  c.rstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+  c.scale = gamma * c.rstd;
+  c.shift = beta - c.mean * c.scale;
+  return c;
+}
+__device__ __forceinline__ BnCoef bn_coef_from_running(float rm, float rv, float gamma, float beta) {
+  BnCoef c;
+  c.mean = rm;
+  c.var = rv;
+  c.rstd = 1.0f / sqrtf(rv + kBnEps);
+  c.scale = gamma * c.rstd;
+  c.shift = beta - c.mean * c.scale;
+  return c;
+}
+
+}  // namespace rnvp

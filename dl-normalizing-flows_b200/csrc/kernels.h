@@ -1,0 +1,127 @@
+// Launcher prototypes shared between the kernel translation units and the runtime.
+// Everything here is internal; the public surface is include/rnvp.h.
+#pragma once
+#include "common.cuh"
+
+namespace rnvp {
+
+// ---- layout (flow_realnvp.py:121-193), all NHWC ---------------------------------
+enum PermMode {
+  PERM_SQUEEZE = 0,      // hi [B,2s,2s,C]            -> sq [B,s,s,4C]
+  PERM_UNDO_SQUEEZE,     // sq                         -> hi
+  PERM_FACTOR_OUT,       // hi                         -> on,off [B,s,s,2C]
+  PERM_RESTORE,          // on,off                     -> hi
+  PERM_UNSQ_FACTOR,      // sq                         -> on,off   (undo_squeeze o factor_out)
+  PERM_FACTOR_SQ         // on,off                     -> sq       (restore o squeeze)
+};
+// s = low-res side, C = channels of the high-res tensor
+int k_permute(PermMode mode, const float* hi, const float* sq, const float* on, const float* off,
+              float* hi_o, float* sq_o, float* on_o, float* off_o, int B, int s, int C, cudaStream_t st);
+int k_nchw_to_nhwc(const float* in, float* out, int B, int C, int H, int W, cudaStream_t st);
+int k_nhwc_to_nchw(const float* in, float* out, int B, int C, int H, int W, cudaStream_t st);
+
+// ---- logit (utils.py:33-72) -----------------------------------------------------
+int k_logit_fwd(const float* xf, const uint8_t* xu8, const float* noise, float* y, float* logdet,
+                int B, int n, float constraint, uint64_t seed, uint64_t offset, cudaStream_t st);
+int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream_t st);
+
+// ---- batch norm on [P,ld] trunk tensors (C real channels, C % 4 == 0, ld = pad32(C)) ---
+// h = relu(gamma*(x-mean)*rstd+beta).
+//   mode 1 (training): (sum,sumsq) over `count` values come from `sums` (2C doubles);
+//           save[4C] = mean,rstd,scale,shift; running stats updated by block 0
+//   mode 0 (eval): running statistics
+//   mode 2 (recompute in backward): scale/shift read back from `save`
+int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
+              const float* gamma, const float* beta, float* run_mean, float* run_var,
+              float* save, int mode, cudaStream_t st);
+// gm = g * 1[h>0] written to gm_out; sums2[0:C] += sum gm, sums2[C:2C] += sum gm*xhat
+int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C, int ld,
+                    const float* save, double* sums2, cudaStream_t st);
+// dx (= or +=) gamma*rstd*(gm - m1 - xhat*m2); block 0 adds dgamma/dbeta
+int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
+                   const float* save, const double* sums2, double count, const float* gamma,
+                   float* dgamma, float* dbeta, cudaStream_t st);
+
+// ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
+int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
+int k_cpl_in_build(const float* x, CplGeom g, const double* sums, double count, const float* gamma,
+                   const float* beta, float* run_mean, float* run_var, float* save, int training,
+                   float* h0, cudaStream_t st);
+int k_cpl_fwd_a(const float* x, const float* stt, CplGeom g, const float* scale, const float* sshift,
+                float* xprime, double* sums, double* logdet_acc, int training, cudaStream_t st);
+int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g, const double* sums,
+                double count, float* run_mean, float* run_var, float* save, int training,
+                const float* scale, const float* sshift, float* y, float* logJ, double* logdet_acc,
+                cudaStream_t st);
+int k_cpl_inv(const float* y, const float* stt, CplGeom g, const float* run_mean, const float* run_var,
+              const float* scale, const float* sshift, float* x, cudaStream_t st);
+// sums2: [0:cio] sum g, [cio:2cio] sum g*xhat, [2cio] K = sum_p dll_b(p)*keep_p
+int k_cpl_bwd_a(const float* dy, const float* xprime, CplGeom g, const float* save, const float* dll,
+                double* sums2, cudaStream_t st);
+int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const float* stt, CplGeom g,
+                const float* save, const double* sums2, double count, const float* dll,
+                const float* scale, const float* sshift, float* dst, float* dxdir,
+                float* dscale, float* dsshift, cudaStream_t st);
+int k_cpl_in_bwd_a(const float* dh0, const float* x, CplGeom g, const float* save, double* sums3,
+                   cudaStream_t st);
+int k_cpl_in_bwd_b(const float* dh0, const float* x, const float* dxdir, const float* dy, CplGeom g,
+                   const float* save, const double* sums3, double count, const float* gamma,
+                   float* dgamma, float* dbeta, float* dx, cudaStream_t st);
+
+// ---- prior, per-sample sums ---------------------------------------------------------
+int k_prior_ll(const float* z, int B, int n, float loc, float scale, double* acc, cudaStream_t st);
+int k_prior_grad(const float* z, const float* dll, float* dz, int accumulate, int B, int n, float loc,
+                 float scale, cudaStream_t st);
+int k_finalize_ll(const double* logdet_acc, const double* prior_acc, float* ll, float* logdet, int B,
+                  cudaStream_t st);
+int k_add(float* dst, const float* src, size_t n, cudaStream_t st);
+// out[b] = in[b*n]  (per-sample scalar carried by a broadcast tensor)
+int k_gather_first(const float* in, float* out, int B, int n, cudaStream_t st);
+
+// ---- weight norm (modules_realnvp.py:53-59), batched through a job table ----------
+// Offsets are in floats relative to the weight arena (wf/wb) and the wgrad scratch (dw), both of
+// which live in the caller's workspace, so the table survives a workspace move.
+struct WnJob {
+  const float* v;      // (cout, cin, k, k)
+  const float* g;      // (cout)
+  float* dv;           // grad of v (+=) or null
+  float* dg;           // grad of g (+=) or null when frozen
+  size_t wf_off;       // [taps][npad_f][kpad_f]
+  size_t wb_off;       // [taps][npad_b][kpad_b]
+  size_t dw_off;       // wgrad output, same layout as wf
+  int cout, cin, taps;
+  int npad_f, kpad_f, npad_b, kpad_b;
+};
+// writes every element of wf and wb (zero in the padding), so the arena needs no clearing
+int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, cudaStream_t st);
+int k_weightnorm_bwd(const WnJob* jobs_dev, int njobs, int max_cout, const float* wbase,
+                     const float* dwbase, cudaStream_t st);
+
+struct Seg { const float* p; float* g; int n; };
+int k_sumsq(const Seg* segs_dev, int nsegs, double* acc, cudaStream_t st);      // acc += sum p^2
+int k_sumsq_finish(const double* acc, float* out, cudaStream_t st);
+int k_sumsq_bwd(const Seg* segs_dev, int nsegs, const float* dws_dev, cudaStream_t st);   // g += 2*p*dws
+
+// ---- convolutions -------------------------------------------------------------------
+struct ConvArgs {
+  const float* x;      // [B,S,S,kpad] activated input
+  const float* w;      // [taps][npad][kpad]
+  const float* bias;   // [n] or null
+  const float* res;    // [P,ldy] or null; may alias y
+  float* y;            // [P,ldy]
+  double* stats;       // [2n] or null
+  int B, S, kpad, n, npad, taps, ldy;
+};
+int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
+int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
+struct WgradArgs {
+  const float* x;      // [B,S,S,kpad]
+  const float* dy;     // [P,lddy]
+  float* dw;           // [taps][npad][kpad]  (+=)
+  float* dbias;        // [n] (+=) or null
+  int B, S, kpad, n, npad, taps, lddy;
+};
+int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st);
+int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st);
+
+}  // namespace rnvp

@@ -1,0 +1,1102 @@
+// Host-side runtime of the RealNVP hot path: the plan (topology + parameter table), the
+// workspace layout, and the launch schedules for one coupling and for the whole multi-scale
+// stack, forward / inverse / backward.  Everything is issued on the caller's stream; nothing
+// here synchronises, allocates per call or touches the host after rnvp_plan_bind, so a whole
+// step can be captured in a CUDA graph by the caller.
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "kernels.h"
+
+namespace rnvp {
+const char* get_error();
+int dp_allreduce_doubles(rnvp_plan* plan, double* buf, size_t n, cudaStream_t st);   // dp.cu
+}
+using namespace rnvp;
+
+// =====================================================================================
+// plan
+// =====================================================================================
+namespace {
+
+struct ConvDesc {
+  int cin, cout, taps;
+  bool has_bias, train_g;
+  int kpad, npad;        // forward operand  wf [taps][npad][kpad]
+  int kpad_b, npad_b;    // dgrad operand    wb [taps][npad_b][kpad_b]
+  size_t wf_off, wb_off; // float offsets inside the weight arena
+  size_t dw_off;         // float offset inside the per-coupling wgrad scratch
+  int slot_v, slot_g, slot_bias;   // slots relative to the coupling
+};
+struct BnDesc {
+  int C;
+  int slot_w, slot_b, slot_rm, slot_rv;
+  size_t sf, sb;         // double offsets of forward / backward sums (2C each)
+  size_t save;           // float offset of (mean, rstd, scale, shift) [4C]
+};
+struct CouplingDesc {
+  std::string name;
+  int kind, C, S, D, cfg;          // kind 0 = checkerboard, 1 = channelwise
+  int cio, cin, cin_pad, cst, cst_pad, ldD;
+  std::vector<ConvDesc> convs;     // in_block, in_skip, [rb0, rb3, rb6, core_skip] x R, out
+  std::vector<BnDesc> bns;         // [bn1, bn2, bn3] x R, out_block.0
+  size_t sf_in, sf_out, sb_cpl, sb_in;   // double offsets
+  size_t save_in, save_out;              // float offsets
+  int job0;                              // first weight-norm job
+  size_t dw_floats;                      // wgrad scratch this coupling needs
+  CplGeom geom(int B) const {
+    CplGeom g;
+    g.B = B; g.S = S; g.C = C; g.cio = cio;
+    g.ckbd = kind == 0; g.cfg = cfg;
+    if (kind == 0) { g.on_off = 0; g.in_off = 0; }
+    else if (cfg) { g.on_off = 0; g.in_off = C / 2; }      // modules_realnvp.py:333-336
+    else { g.on_off = C / 2; g.in_off = 0; }
+    g.cin_pad = cin_pad; g.cst_pad = cst_pad;
+    return g;
+  }
+};
+
+enum { SLOT_SCALE = 0, SLOT_SSHIFT, SLOT_INBN_W, SLOT_INBN_B, SLOT_INBN_RM, SLOT_INBN_RV,
+       SLOT_OUTBN_RM, SLOT_OUTBN_RV, SLOT_CONV0 };
+
+constexpr int kMaxR = 16;
+
+// float offsets (relative to the activation base of one coupling) of everything a coupling keeps
+struct CplAct {
+  size_t h0, a[kMaxR + 1], u1[kMaxR], u2[kMaxR], skip, st, xprime, y, total;
+};
+
+struct Layout {
+  size_t weights, dw, accum, stats_f, stats_b, saves, flow, act, scratch, total;   // byte offsets
+  size_t stats_f_bytes, stats_b_bytes;
+  std::vector<size_t> cpl_act;       // byte offset of each coupling's activation block
+  // flow-level buffers (float counts)
+  size_t img;                        // B*C*H*W
+};
+
+}  // namespace
+
+struct rnvp_plan {
+  rnvp_config cfg;
+  std::vector<CouplingDesc> cpl;
+  std::vector<std::string> slot_names;
+  int slots_per_coupling = 0;
+  std::vector<void*> params, grads;
+  size_t weight_floats = 0, dw_floats = 0, stats_f_doubles = 0, stats_b_doubles = 0, save_floats = 0;
+  WnJob* d_jobs = nullptr;
+  std::vector<WnJob> h_jobs;
+  int max_cout = 0;
+  Seg* d_segs = nullptr;
+  int nsegs = 0;
+  int math = RNVP_MATH_FP32;
+  bool bound = false;
+  bool single = false;               // one stand-alone coupling (rnvp_plan_create_single)
+  // data parallel
+  void* comm = nullptr;
+  int rank = 0, world = 1;
+  // forward bookkeeping for backward
+  int saved_batch = -1;
+  int saved_coupling = -1;           // >=0: a stand-alone coupling forward was saved
+  std::vector<const float*> x_in;    // input of each coupling in the last training forward
+};
+
+namespace {
+
+template <typename T> inline T* P_(const rnvp_plan* p, const CouplingDesc& c, int ci, int slot) {
+  (void)c;
+  return reinterpret_cast<T*>(p->params[(size_t)ci * p->slots_per_coupling + slot]);
+}
+inline float* G_(const rnvp_plan* p, int ci, int slot) {
+  return reinterpret_cast<float*>(p->grads[(size_t)ci * p->slots_per_coupling + slot]);
+}
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+ConvDesc make_conv(int cin, int cout, int k, bool bias, bool train_g, int& slot, std::vector<std::string>& names,
+                   const std::string& prefix, bool record) {
+  ConvDesc c{};
+  c.cin = cin; c.cout = cout; c.taps = k * k; c.has_bias = bias; c.train_g = train_g;
+  c.kpad = pad_to(cin, 32); c.npad = pad_to(cout, 16);
+  c.kpad_b = pad_to(cout, 32); c.npad_b = pad_to(cin, 16);
+  c.slot_v = slot++; c.slot_g = slot++; c.slot_bias = slot++;
+  if (record) {
+    names.push_back(prefix + ".conv.weight_v");
+    names.push_back(prefix + ".conv.weight_g");
+    names.push_back(bias ? prefix + ".conv.bias" : std::string());
+  }
+  return c;
+}
+BnDesc make_bn(int C, int& slot, std::vector<std::string>& names, const std::string& prefix, bool record) {
+  BnDesc b{};
+  b.C = C;
+  b.slot_w = slot++; b.slot_b = slot++; b.slot_rm = slot++; b.slot_rv = slot++;
+  if (record) {
+    names.push_back(prefix + ".weight");
+    names.push_back(prefix + ".bias");
+    names.push_back(prefix + ".running_mean");
+    names.push_back(prefix + ".running_var");
+  }
+  return b;
+}
+
+struct SingleSpec { int kind, C, S, D, cfg; };
+
+int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
+  const rnvp_config& c = p->cfg;
+  RNVP_REQUIRE(c.num_scales >= 1 && c.res_blocks >= 1 && c.res_blocks <= kMaxR,
+               "num_scales=%d res_blocks=%d unsupported (res_blocks must be in [1,%d])", c.num_scales,
+               c.res_blocks, kMaxR);
+  RNVP_REQUIRE(c.base_dim > 0 && c.base_dim % 4 == 0, "base_dim=%d must be a positive multiple of 4", c.base_dim);
+  RNVP_REQUIRE(c.channels > 0 && c.image_size > 0, "bad channels/image_size");
+  RNVP_REQUIRE(single || c.image_size % (1 << (c.num_scales - 1)) == 0, "image_size=%d not divisible by 2^%d",
+               c.image_size, c.num_scales - 1);
+  RNVP_REQUIRE(c.prior_scale > 0.f, "prior scale must be positive");
+  const int R = c.res_blocks;
+  int chan = c.channels, size = c.image_size, dim = c.base_dim;
+  auto add = [&](const std::string& name, int kind, int C, int S, int D, int cfg) {
+    CouplingDesc d;
+    d.name = name; d.kind = kind; d.C = C; d.S = S; d.D = D; d.cfg = cfg;
+    d.cio = kind == 0 ? C : C / 2;
+    d.cin = kind == 0 ? 2 * C + 1 : C;              // modules_realnvp.py:260, 320
+    d.cin_pad = pad_to(d.cin, 32);
+    d.cst = 2 * d.cio;
+    d.cst_pad = pad_to(d.cst, 32);
+    d.ldD = pad_to(D, 32);
+    bool rec = p->cpl.empty();
+    int slot = SLOT_CONV0;
+    if (rec) {
+      p->slot_names = {"scale", "scale_shift", "in_bn.weight", "in_bn.bias", "in_bn.running_mean",
+                       "in_bn.running_var", "out_bn.running_mean", "out_bn.running_var"};
+    }
+    const std::string b1 = "block.1";
+    d.convs.push_back(make_conv(d.cin, D, 3, true, false, slot, p->slot_names, b1 + ".in_block", rec));
+    d.convs.push_back(make_conv(D, D, 1, true, true, slot, p->slot_names, b1 + ".in_skip", rec));
+    for (int i = 0; i < R; ++i) {
+      std::string cb = b1 + ".core_block." + std::to_string(i);
+      d.convs.push_back(make_conv(D, D, 1, false, false, slot, p->slot_names, cb + ".res_block.0", rec));
+      d.convs.push_back(make_conv(D, D, 3, false, false, slot, p->slot_names, cb + ".res_block.3", rec));
+      d.convs.push_back(make_conv(D, D, 1, true, true, slot, p->slot_names, cb + ".res_block.6", rec));
+      d.convs.push_back(make_conv(D, D, 1, true, true, slot, p->slot_names,
+                                  b1 + ".core_skips." + std::to_string(i), rec));
+    }
+    d.convs.push_back(make_conv(D, d.cst, 1, true, true, slot, p->slot_names, b1 + ".out_block.2", rec));
+    for (int i = 0; i < R; ++i) {
+      std::string cb = b1 + ".core_block." + std::to_string(i);
+      d.bns.push_back(make_bn(D, slot, p->slot_names, cb + ".in_block.0", rec));
+      d.bns.push_back(make_bn(D, slot, p->slot_names, cb + ".res_block.1", rec));
+      d.bns.push_back(make_bn(D, slot, p->slot_names, cb + ".res_block.4", rec));
+    }
+    d.bns.push_back(make_bn(D, slot, p->slot_names, b1 + ".out_block.0", rec));
+    if (rec) p->slots_per_coupling = slot;
+    p->cpl.push_back(d);
+  };
+  if (single) {
+    RNVP_REQUIRE(single->kind == 0 || single->C % 2 == 0, "channelwise coupling needs an even channel count");
+    add(single->kind == 0 ? "ckbd" : "chan", single->kind, single->C, single->S, single->D, single->cfg ? 1 : 0);
+  }
+  for (int s = 1; !single && s < c.num_scales; ++s) {
+    const int ck[3] = {1, 0, 1}, ch[3] = {0, 1, 0};               // flow_realnvp.py:107-116
+    for (int i = 0; i < 3; ++i)
+      add("s" + std::to_string(s) + "_ckbd." + std::to_string(i), 0, chan, size, dim, ck[i]);
+    for (int i = 0; i < 3; ++i)
+      add("s" + std::to_string(s) + "_chan." + std::to_string(i), 1, chan * 4, size / 2, dim * 2, ch[i]);
+    chan *= 2; size /= 2; dim *= 2;
+  }
+  const int fin[4] = {1, 0, 1, 0};                                 // flow_realnvp.py:100-105
+  for (int i = 0; !single && i < 4; ++i)
+    add("s" + std::to_string(c.num_scales) + "_ckbd." + std::to_string(i), 0, chan, size, dim, fin[i]);
+
+  // arenas independent of the batch size
+  size_t wo = 0, sf = 0, sb = 0, sv = 0;
+  int job = 0;
+  for (auto& d : p->cpl) {
+    RNVP_REQUIRE(d.cio <= 256, "coupling %s: %d channels unsupported", d.name.c_str(), d.cio);
+    RNVP_REQUIRE(d.ldD / 4 <= 256, "coupling %s: D=%d unsupported (max 1024)", d.name.c_str(), d.D);
+    d.job0 = job;
+    size_t dwo = 0;
+    for (auto& cv : d.convs) {
+      cv.wf_off = wo; wo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
+      cv.wb_off = wo; wo += align_up((size_t)cv.taps * cv.npad_b * cv.kpad_b, 64);
+      cv.dw_off = dwo; dwo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
+      p->max_cout = std::max(p->max_cout, cv.cout);
+      ++job;
+    }
+    d.dw_floats = dwo;
+    p->dw_floats = std::max(p->dw_floats, dwo);
+    d.sf_in = sf; sf += 2 * d.cio;
+    d.sf_out = sf; sf += 2 * d.cio;
+    d.sb_cpl = sb; sb += 2 * d.cio + 2;
+    d.sb_in = sb; sb += 2 * d.cio;
+    d.save_in = sv; sv += 4 * d.cio;
+    d.save_out = sv; sv += 2 * d.cio;
+    for (auto& b : d.bns) {
+      b.sf = sf; sf += 2 * b.C;
+      b.sb = sb; sb += 2 * b.C;
+      b.save = sv; sv += 4 * b.C;
+    }
+  }
+  p->weight_floats = wo;
+  p->stats_f_doubles = sf;
+  p->stats_b_doubles = sb;
+  p->save_floats = sv;
+  size_t total = p->cpl.size() * (size_t)p->slots_per_coupling;
+  p->params.assign(total, nullptr);
+  p->grads.assign(total, nullptr);
+  p->x_in.assign(p->cpl.size(), nullptr);
+  return RNVP_OK;
+}
+
+CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
+  CplAct a{};
+  const int R = p->cfg.res_blocks;
+  size_t Pn = (size_t)B * d.S * d.S, o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += align_up(n, 64); return r; };
+  a.h0 = take(Pn * d.cin_pad);
+  if (mode == 1) {
+    for (int i = 0; i <= R; ++i) a.a[i] = take(Pn * d.ldD);
+    for (int i = 0; i < R; ++i) { a.u1[i] = take(Pn * d.ldD); a.u2[i] = take(Pn * d.ldD); }
+  } else {                               // inference: the trunk is updated in place
+    size_t aa = take(Pn * d.ldD), uu = take(Pn * d.ldD);
+    for (int i = 0; i <= R; ++i) a.a[i] = aa;
+    for (int i = 0; i < R; ++i) { a.u1[i] = uu; a.u2[i] = uu; }
+  }
+  a.skip = take(Pn * d.ldD);
+  a.st = take(Pn * d.cst_pad);
+  a.xprime = take(Pn * d.cio);
+  a.y = take(Pn * d.C);
+  a.total = o;
+  return a;
+}
+
+Layout compute_layout(const rnvp_plan* p, int B, int mode) {
+  Layout L{};
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
+  L.weights = take(p->weight_floats * 4);
+  L.dw = take(mode == 1 ? p->dw_floats * 4 : 0);
+  L.accum = take((32 + 2 * (size_t)B) * 8);
+  L.stats_f_bytes = p->stats_f_doubles * 8;
+  L.stats_b_bytes = p->stats_b_doubles * 8;
+  L.stats_f = take(L.stats_f_bytes);
+  L.stats_b = take(mode == 1 ? L.stats_b_bytes : 0);
+  L.saves = take(p->save_floats * 4);
+  const rnvp_config& c = p->cfg;
+  L.img = (size_t)B * c.channels * c.image_size * c.image_size;
+  // flow-level buffers (see flow_bufs): persistent group inputs + factored-out halves (< 5 img),
+  // two forward temporaries, three gradient temporaries, one per-sample vector
+  L.flow = take((L.img * 12 + 64 * p->cfg.num_scales + (size_t)B + 1024) * 4);
+  size_t maxact = 0, maxPD = 0, maxaux = 0;
+  L.cpl_act.resize(p->cpl.size());
+  size_t act_total = 0;
+  for (size_t i = 0; i < p->cpl.size(); ++i) {
+    const CouplingDesc& d = p->cpl[i];
+    CplAct a = cpl_act(p, d, B, mode);
+    L.cpl_act[i] = act_total * 4;
+    if (mode == 1) act_total += align_up(a.total, 256);
+    maxact = std::max(maxact, a.total);
+    size_t Pn = (size_t)B * d.S * d.S;
+    maxPD = std::max(maxPD, align_up(Pn * d.ldD, 64));
+    maxaux = std::max(maxaux, align_up(Pn * d.cst_pad, 64) + align_up(Pn * d.cio, 64) + align_up(Pn * d.cin_pad, 64));
+  }
+  if (mode != 1) act_total = align_up(maxact, 256);
+  L.act = take(act_total * 4);
+  for (auto& v : L.cpl_act) v += L.act;
+  // scratch: H + (mode 1: T0, T1, DA, DO + dst/dxdir/dh0)
+  L.scratch = take((mode == 1 ? 5 * maxPD + maxaux : maxPD) * 4);
+  L.total = o;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------
+// execution context of one call
+// ------------------------------------------------------------------------------------
+struct Ctx {
+  rnvp_plan* p;
+  Layout L;
+  char* ws;
+  int B, mode;
+  cudaStream_t st;
+  float* weights() const { return reinterpret_cast<float*>(ws + L.weights); }
+  float* dw() const { return reinterpret_cast<float*>(ws + L.dw); }
+  double* ws_acc() const { return reinterpret_cast<double*>(ws + L.accum); }
+  double* logdet_acc() const { return reinterpret_cast<double*>(ws + L.accum) + 32; }
+  double* prior_acc() const { return logdet_acc() + B; }
+  double* sf(size_t off) const { return reinterpret_cast<double*>(ws + L.stats_f) + off; }
+  double* sb(size_t off) const { return reinterpret_cast<double*>(ws + L.stats_b) + off; }
+  float* save(size_t off) const { return reinterpret_cast<float*>(ws + L.saves) + off; }
+  float* act(int ci, size_t off) const { return reinterpret_cast<float*>(ws + L.cpl_act[ci]) + off; }
+  float* scratch() const { return reinterpret_cast<float*>(ws + L.scratch); }
+};
+
+int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* stream, Ctx* c) {
+  RNVP_REQUIRE(p && p->bound, "plan is not bound to parameters (call rnvp_plan_bind)");
+  RNVP_REQUIRE(B > 0, "batch must be positive");
+  c->p = p; c->B = B; c->mode = mode; c->st = (cudaStream_t)stream;
+  c->L = compute_layout(p, B, mode);
+  if (ws == nullptr || ws_bytes < c->L.total) {
+    set_error("workspace too small: need %zu bytes, got %zu", c->L.total, ws_bytes);
+    return RNVP_ERR_WORKSPACE;
+  }
+  RNVP_REQUIRE(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  c->ws = reinterpret_cast<char*>(ws);
+  return RNVP_OK;
+}
+
+int sync_stats(const Ctx& c, double* buf, size_t n) {
+  if (c.p->world > 1) return dp_allreduce_doubles(c.p, buf, n, c.st);
+  return RNVP_OK;
+}
+
+int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
+             const float* bias, const float* res, double* stats) {
+  ConvArgs a{};
+  a.x = x;
+  a.w = c.weights() + (dgrad ? cv.wb_off : cv.wf_off);
+  a.bias = bias; a.res = res; a.y = y; a.stats = stats;
+  a.B = c.B; a.S = S;
+  a.kpad = dgrad ? cv.kpad_b : cv.kpad;
+  a.n = dgrad ? cv.cin : cv.cout;
+  a.npad = dgrad ? cv.npad_b : cv.npad;
+  a.taps = cv.taps; a.ldy = ldy;
+  return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
+}
+int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy, int lddy, int S, float* dbias) {
+  WgradArgs a{};
+  a.x = x; a.dy = dy; a.dw = c.dw() + cv.dw_off; a.dbias = dbias;
+  a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
+  return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.st) : k_conv_wgrad_fp32(a, c.st);
+}
+
+// ------------------------------------------------------------------------------------
+// s/t network (ResidualModule, modules_realnvp.py:175-194) forward
+// ------------------------------------------------------------------------------------
+int net_forward(const Ctx& c, int ci, int training) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  const int R = p->cfg.res_blocks, S = d.S, ld = d.ldD, Pn = c.B * S * S;
+  const double count = (double)Pn * p->world;
+  CplAct A = cpl_act(p, d, c.B, c.mode);
+  float* H = c.scratch();
+  auto bias = [&](const ConvDesc& cv) { return cv.has_bias ? P_<float>(p, d, ci, cv.slot_bias) : nullptr; };
+  auto bn = [&](int bi, const float* x) -> int {
+    const BnDesc& b = d.bns[bi];
+    if (training) RNVP_TRY(sync_stats(c, c.sf(b.sf), 2 * b.C));
+    return k_bn_relu(x, H, Pn, b.C, ld, training ? c.sf(b.sf) : nullptr, count, P_<float>(p, d, ci, b.slot_w),
+                     P_<float>(p, d, ci, b.slot_b), P_<float>(p, d, ci, b.slot_rm),
+                     P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, c.st);
+  };
+  auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
+  const ConvDesc* cv = d.convs.data();
+  // a0 = in_block(h0); skip = in_skip(a0)
+  RNVP_TRY(run_conv(c, cv[0], false, c.act(ci, A.h0), S, c.act(ci, A.a[0]), ld, bias(cv[0]), nullptr, st_of(0)));
+  RNVP_TRY(run_conv(c, cv[1], false, c.act(ci, A.a[0]), S, c.act(ci, A.skip), ld, bias(cv[1]), nullptr, nullptr));
+  for (int i = 0; i < R; ++i) {
+    const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
+    float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
+    RNVP_TRY(bn(3 * i, ai));
+    RNVP_TRY(run_conv(c, *rb0, false, H, S, c.act(ci, A.u1[i]), ld, nullptr, nullptr, st_of(3 * i + 1)));
+    RNVP_TRY(bn(3 * i + 1, c.act(ci, A.u1[i])));
+    RNVP_TRY(run_conv(c, *rb3, false, H, S, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2)));
+    RNVP_TRY(bn(3 * i + 2, c.act(ci, A.u2[i])));
+    RNVP_TRY(run_conv(c, *rb6, false, H, S, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr));
+    RNVP_TRY(run_conv(c, *cs, false, an, S, c.act(ci, A.skip), ld, bias(*cs), c.act(ci, A.skip),
+                      i == R - 1 ? st_of(3 * R) : nullptr));
+  }
+  RNVP_TRY(bn(3 * R, c.act(ci, A.skip)));
+  const ConvDesc& oc = cv[2 + 4 * R];
+  RNVP_TRY(run_conv(c, oc, false, H, S, c.act(ci, A.st), d.cst_pad, bias(oc), nullptr, nullptr));
+  return RNVP_OK;
+}
+
+// backward of the s/t network: dst [P,cst_pad] -> dh0 [P,cin_pad]; weight grads into the dw scratch
+int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  const int R = p->cfg.res_blocks, S = d.S, ld = d.ldD, Pn = c.B * S * S;
+  const double count = (double)Pn * p->world;
+  CplAct A = cpl_act(p, d, c.B, c.mode);
+  size_t PD = align_up((size_t)Pn * ld, 64);
+  size_t maxPD = 0;
+  for (auto& q : p->cpl) maxPD = std::max(maxPD, align_up((size_t)c.B * q.S * q.S * q.ldD, 64));
+  (void)PD;
+  float* H = c.scratch();
+  float* T0 = H + maxPD;
+  float* T1 = T0 + maxPD;
+  float* DA = T1 + maxPD;
+  float* DO = DA + maxPD;
+  auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
+  auto recompute = [&](int bi, const float* x) {
+    const BnDesc& b = d.bns[bi];
+    return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2, c.st);
+  };
+  // BN+ReLU backward in place on g: g <- d(pre-BN input); out==nullptr: in place, else (+=) into out
+  auto bn_bwd = [&](int bi, float* g, const float* x, float* out, int accumulate) -> int {
+    const BnDesc& b = d.bns[bi];
+    RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
+    RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
+    return k_bn_bwd_apply(g, x, out ? out : g, accumulate, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
+                          P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b), c.st);
+  };
+  const ConvDesc* cv = d.convs.data();
+  const ConvDesc& oc = cv[2 + 4 * R];
+  // out_block: st = conv(relu(bn(skip)))
+  RNVP_TRY(recompute(3 * R, c.act(ci, A.skip)));
+  RNVP_TRY(run_wgrad(c, oc, H, dst, d.cst_pad, S, gbias(oc)));
+  RNVP_TRY(run_conv(c, oc, true, dst, S, T0, ld, nullptr, nullptr, nullptr));
+  RNVP_TRY(bn_bwd(3 * R, T0, c.act(ci, A.skip), DO, 0));
+  for (int i = R - 1; i >= 0; --i) {
+    const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
+    float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
+    float *u1 = c.act(ci, A.u1[i]), *u2 = c.act(ci, A.u2[i]);
+    // skip += core_skip_i(a_{i+1})
+    RNVP_TRY(run_wgrad(c, *cs, an, DO, ld, S, gbias(*cs)));
+    RNVP_TRY(run_conv(c, *cs, true, DO, S, DA, ld, nullptr, i == R - 1 ? nullptr : DA, nullptr));
+    // a_{i+1} = a_i + rb6(relu(bn3(u2)))
+    RNVP_TRY(recompute(3 * i + 2, u2));
+    RNVP_TRY(run_wgrad(c, *rb6, H, DA, ld, S, gbias(*rb6)));
+    RNVP_TRY(run_conv(c, *rb6, true, DA, S, T0, ld, nullptr, nullptr, nullptr));
+    RNVP_TRY(bn_bwd(3 * i + 2, T0, u2, nullptr, 0));
+    // u2 = rb3(relu(bn2(u1)))
+    RNVP_TRY(recompute(3 * i + 1, u1));
+    RNVP_TRY(run_wgrad(c, *rb3, H, T0, ld, S, nullptr));
+    RNVP_TRY(run_conv(c, *rb3, true, T0, S, T1, ld, nullptr, nullptr, nullptr));
+    RNVP_TRY(bn_bwd(3 * i + 1, T1, u1, nullptr, 0));
+    // u1 = rb0(relu(bn1(a_i)))
+    RNVP_TRY(recompute(3 * i, ai));
+    RNVP_TRY(run_wgrad(c, *rb0, H, T1, ld, S, nullptr));
+    RNVP_TRY(run_conv(c, *rb0, true, T1, S, T0, ld, nullptr, nullptr, nullptr));
+    RNVP_TRY(bn_bwd(3 * i, T0, ai, DA, 1));
+  }
+  // skip = in_skip(a0) (+...); a0 = in_block(h0)
+  RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));
+  RNVP_TRY(run_conv(c, cv[1], true, DO, S, DA, ld, nullptr, DA, nullptr));
+  RNVP_TRY(run_wgrad(c, cv[0], c.act(ci, A.h0), DA, ld, S, gbias(cv[0])));
+  RNVP_TRY(run_conv(c, cv[0], true, DA, S, dh0, d.cin_pad, nullptr, nullptr, nullptr));
+  return RNVP_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// one coupling (NHWC in / out)
+// ------------------------------------------------------------------------------------
+int coupling_forward(const Ctx& c, int ci, const float* x, float* y, float* logJ, int training) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  CplGeom g = d.geom(c.B);
+  CplAct A = cpl_act(p, d, c.B, c.mode);
+  const double count = (double)g.P() * p->world;
+  if (training) {
+    RNVP_TRY(k_cpl_in_stats(x, g, c.sf(d.sf_in), c.st));
+    RNVP_TRY(sync_stats(c, c.sf(d.sf_in), 2 * d.cio));
+  }
+  RNVP_TRY(k_cpl_in_build(x, g, c.sf(d.sf_in), count, P_<float>(p, d, ci, SLOT_INBN_W),
+                          P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
+                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0), c.st));
+  RNVP_TRY(net_forward(c, ci, training));
+  RNVP_TRY(k_cpl_fwd_a(x, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT),
+                       c.act(ci, A.xprime), c.sf(d.sf_out), c.logdet_acc(), training, c.st));
+  if (training) RNVP_TRY(sync_stats(c, c.sf(d.sf_out), 2 * d.cio));
+  RNVP_TRY(k_cpl_fwd_b(c.act(ci, A.xprime), x, c.act(ci, A.st), g, c.sf(d.sf_out), count,
+                       P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
+                       c.save(d.save_out), training, P_<float>(p, d, ci, SLOT_SCALE),
+                       P_<float>(p, d, ci, SLOT_SSHIFT), y, logJ, c.logdet_acc(), c.st));
+  if (training) p->x_in[ci] = x;
+  return RNVP_OK;
+}
+
+int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int training) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  CplGeom g = d.geom(c.B);
+  CplAct A = cpl_act(p, d, c.B, c.mode);
+  const double count = (double)g.P() * p->world;
+  if (training) {
+    RNVP_TRY(k_cpl_in_stats(y, g, c.sf(d.sf_in), c.st));
+    RNVP_TRY(sync_stats(c, c.sf(d.sf_in), 2 * d.cio));
+  }
+  RNVP_TRY(k_cpl_in_build(y, g, c.sf(d.sf_in), count, P_<float>(p, d, ci, SLOT_INBN_W),
+                          P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
+                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0), c.st));
+  RNVP_TRY(net_forward(c, ci, training));
+  RNVP_TRY(k_cpl_inv(y, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
+                     P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), x, c.st));
+  return RNVP_OK;
+}
+
+// dy -> dx (both NHWC [P,C]); dll (B) = dLoss/dlogdet per sample
+int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, float* dx) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  CplGeom g = d.geom(c.B);
+  CplAct A = cpl_act(p, d, c.B, c.mode);
+  const double count = (double)g.P() * p->world;
+  const float* x = p->x_in[ci];
+  RNVP_REQUIRE(x != nullptr, "coupling %s: backward without a training forward", d.name.c_str());
+  size_t maxPD = 0;
+  for (auto& q : p->cpl) maxPD = std::max(maxPD, align_up((size_t)c.B * q.S * q.S * q.ldD, 64));
+  float* aux = c.scratch() + 5 * maxPD;
+  size_t Pn = g.P();
+  float* dst = aux;
+  float* dxdir = dst + align_up(Pn * d.cst_pad, 64);
+  float* dh0 = dxdir + align_up(Pn * d.cio, 64);
+  RNVP_CUDA(cudaMemsetAsync(c.dw(), 0, d.dw_floats * 4, c.st));
+  RNVP_TRY(k_cpl_bwd_a(dy, c.act(ci, A.xprime), g, c.save(d.save_out), dll, c.sb(d.sb_cpl), c.st));
+  RNVP_TRY(sync_stats(c, c.sb(d.sb_cpl), 2 * d.cio + 1));
+  RNVP_TRY(k_cpl_bwd_b(dy, c.act(ci, A.xprime), x, c.act(ci, A.st), g, c.save(d.save_out), c.sb(d.sb_cpl), count,
+                       dll, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), dst, dxdir,
+                       G_(p, ci, SLOT_SCALE), G_(p, ci, SLOT_SSHIFT), c.st));
+  RNVP_TRY(net_backward(c, ci, dst, dh0));
+  RNVP_TRY(k_cpl_in_bwd_a(dh0, x, g, c.save(d.save_in), c.sb(d.sb_in), c.st));
+  RNVP_TRY(sync_stats(c, c.sb(d.sb_in), 2 * d.cio));
+  RNVP_TRY(k_cpl_in_bwd_b(dh0, x, dxdir, dy, g, c.save(d.save_in), c.sb(d.sb_in), count,
+                          P_<float>(p, d, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_B), dx, c.st));
+  RNVP_TRY(k_weightnorm_bwd(p->d_jobs + d.job0, (int)d.convs.size(), p->max_cout, c.weights(), c.dw(), c.st));
+  return RNVP_OK;
+}
+
+int materialize_weights(const Ctx& c, int first_job, int njobs) {
+  return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(), c.st);
+}
+
+int zero_pass(const Ctx& c, bool backward) {
+  if (!backward) {
+    RNVP_CUDA(cudaMemsetAsync(c.ws + c.L.accum, 0, (32 + 2 * (size_t)c.B) * 8, c.st));
+    if (c.L.stats_f_bytes) RNVP_CUDA(cudaMemsetAsync(c.ws + c.L.stats_f, 0, c.L.stats_f_bytes, c.st));
+  } else if (c.L.stats_b_bytes) {
+    RNVP_CUDA(cudaMemsetAsync(c.ws + c.L.stats_b, 0, c.L.stats_b_bytes, c.st));
+  }
+  return RNVP_OK;
+}
+
+// trunk tensors whose channel count is not a multiple of 32 carry zero padding that no kernel
+// writes; clear the activation + scratch region once per call in that (test-sized) case
+int clear_padding(const Ctx& c) {
+  bool need = false;
+  for (auto& d : c.p->cpl) need |= (d.ldD != d.D);
+  if (need) RNVP_CUDA(cudaMemsetAsync(c.ws + c.L.act, 0, c.L.total - c.L.act, c.st));
+  return RNVP_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+const char* rnvp_last_error(void) { return rnvp::get_error(); }
+const char* rnvp_version(void) { return "rnvp-b200 0.1 (sm_100a)"; }
+
+int rnvp_device_ok(void) {
+  int dev = 0;
+  RNVP_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  RNVP_CUDA(cudaGetDeviceProperties(&prop, dev));
+  RNVP_REQUIRE(prop.major == 10, "device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor);
+  return RNVP_OK;
+}
+
+int rnvp_plan_create(const rnvp_config* cfg, rnvp_plan** out) {
+  RNVP_REQUIRE(cfg && out, "null argument");
+  rnvp_plan* p = new rnvp_plan();
+  p->cfg = *cfg;
+  int s = build_plan(p);
+  if (s != RNVP_OK) {
+    delete p;
+    return s;
+  }
+  *out = p;
+  return RNVP_OK;
+}
+
+int rnvp_plan_create_single(int kind, int C, int S, int D, int mask_cfg, int res_blocks, rnvp_plan** out) {
+  RNVP_REQUIRE(out && (kind == 0 || kind == 1) && C > 0 && S > 0, "bad coupling description");
+  rnvp_plan* p = new rnvp_plan();
+  p->cfg = rnvp_config{C, S, D, res_blocks, 1, 0.f, 1.f};
+  p->single = true;
+  SingleSpec sp{kind, C, S, D, mask_cfg};
+  int s = build_plan(p, &sp);
+  if (s != RNVP_OK) {
+    delete p;
+    return s;
+  }
+  *out = p;
+  return RNVP_OK;
+}
+
+int rnvp_plan_destroy(rnvp_plan* p) {
+  if (!p) return RNVP_OK;
+  if (p->d_jobs) cudaFree(p->d_jobs);
+  if (p->d_segs) cudaFree(p->d_segs);
+  delete p;
+  return RNVP_OK;
+}
+
+int rnvp_plan_num_couplings(const rnvp_plan* p) { return p ? (int)p->cpl.size() : 0; }
+int rnvp_plan_slots_per_coupling(const rnvp_plan* p) { return p ? p->slots_per_coupling : 0; }
+const char* rnvp_plan_slot_name(const rnvp_plan* p, int slot) {
+  if (!p || slot < 0 || slot >= (int)p->slot_names.size()) return nullptr;
+  return p->slot_names[slot].c_str();
+}
+int rnvp_plan_coupling_info(const rnvp_plan* p, int i, char* name, int name_len, int* kind, int* C, int* S,
+                            int* D, int* mask_cfg) {
+  RNVP_REQUIRE(p && i >= 0 && i < (int)p->cpl.size(), "coupling index out of range");
+  const CouplingDesc& d = p->cpl[i];
+  if (name && name_len > 0) snprintf(name, name_len, "%s", d.name.c_str());
+  if (kind) *kind = d.kind;
+  if (C) *C = d.C;
+  if (S) *S = d.S;
+  if (D) *D = d.D;
+  if (mask_cfg) *mask_cfg = d.cfg;
+  return RNVP_OK;
+}
+
+int rnvp_plan_set_math(rnvp_plan* p, int math) {
+  RNVP_REQUIRE(p, "null plan");
+  RNVP_REQUIRE(math == RNVP_MATH_FP32 || math == RNVP_MATH_TF32, "unknown math mode %d", math);
+  p->math = math;
+  return RNVP_OK;
+}
+
+int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* stream) {
+  RNVP_REQUIRE(p && params, "null argument");
+  size_t total = p->cpl.size() * (size_t)p->slots_per_coupling;
+  for (size_t i = 0; i < total; ++i) {
+    p->params[i] = params[i];
+    p->grads[i] = grads ? grads[i] : nullptr;
+  }
+  std::vector<WnJob> jobs;
+  std::vector<Seg> segs;
+  for (size_t ci = 0; ci < p->cpl.size(); ++ci) {
+    const CouplingDesc& d = p->cpl[ci];
+    size_t base = ci * p->slots_per_coupling;
+    for (int s = 0; s < p->slots_per_coupling; ++s) {
+      if (p->slot_names[s].empty()) continue;        // bias slot of a bias-free conv
+      RNVP_REQUIRE(p->params[base + s] != nullptr, "coupling %s: parameter '%s' is null", d.name.c_str(),
+                   p->slot_names[s].c_str());
+    }
+    segs.push_back(Seg{(const float*)p->params[base + SLOT_SCALE], (float*)p->grads[base + SLOT_SCALE], 1});
+    for (const ConvDesc& cv : d.convs) {
+      WnJob j{};
+      j.v = (const float*)p->params[base + cv.slot_v];
+      j.g = (const float*)p->params[base + cv.slot_g];
+      j.dv = (float*)p->grads[base + cv.slot_v];
+      j.dg = cv.train_g ? (float*)p->grads[base + cv.slot_g] : nullptr;
+      j.wf_off = cv.wf_off; j.wb_off = cv.wb_off; j.dw_off = cv.dw_off;
+      j.cout = cv.cout; j.cin = cv.cin; j.taps = cv.taps;
+      j.npad_f = cv.npad; j.kpad_f = cv.kpad; j.npad_b = cv.npad_b; j.kpad_b = cv.kpad_b;
+      jobs.push_back(j);
+      if (cv.train_g) segs.push_back(Seg{j.g, (float*)p->grads[base + cv.slot_g], cv.cout});
+    }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p->d_jobs) RNVP_CUDA(cudaMalloc(&p->d_jobs, jobs.size() * sizeof(WnJob)));
+  if (!p->d_segs) RNVP_CUDA(cudaMalloc(&p->d_segs, segs.size() * sizeof(Seg)));
+  RNVP_CUDA(cudaMemcpyAsync(p->d_jobs, jobs.data(), jobs.size() * sizeof(WnJob), cudaMemcpyHostToDevice, st));
+  RNVP_CUDA(cudaMemcpyAsync(p->d_segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+  RNVP_CUDA(cudaStreamSynchronize(st));
+  p->h_jobs = jobs;
+  p->nsegs = (int)segs.size();
+  p->bound = true;
+  p->saved_batch = -1;
+  p->saved_coupling = -1;
+  return RNVP_OK;
+}
+
+size_t rnvp_plan_workspace_bytes(const rnvp_plan* p, int batch, int mode) {
+  if (!p || batch <= 0) return 0;
+  return compute_layout(p, batch, mode ? 1 : 0).total;
+}
+
+// ---- the flow ------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Flow-level buffers inside the workspace's flow region.  Group inputs and factored-out halves
+// persist from a training forward to its backward.
+struct FlowBufs {
+  std::vector<float*> in_ckbd, in_chan, off;     // index by scale 1..L
+  std::vector<size_t> n;                         // elements of the tensor entering scale s
+  float* T[2];
+  float* G[3];
+  float* dll;
+};
+FlowBufs flow_bufs(const Ctx& c) {
+  const int L = c.p->cfg.num_scales;
+  FlowBufs f;
+  f.in_ckbd.assign(L + 1, nullptr); f.in_chan.assign(L + 1, nullptr); f.off.assign(L + 1, nullptr);
+  f.n.assign(L + 2, 0);
+  float* base = reinterpret_cast<float*>(c.ws + c.L.flow);
+  size_t o = 0;
+  auto take = [&](size_t n) { float* r = base + o; o += align_up(n, 64); return r; };
+  size_t n = c.L.img;
+  for (int s = 1; s <= L; ++s) {
+    f.n[s] = n;
+    f.in_ckbd[s] = take(n);
+    if (s < L) { f.in_chan[s] = take(n); f.off[s] = take(n / 2); }
+    n /= 2;
+  }
+  f.T[0] = take(c.L.img); f.T[1] = take(c.L.img);
+  f.G[0] = take(c.L.img); f.G[1] = take(c.L.img); f.G[2] = take(c.L.img);
+  f.dll = take(c.B);
+  return f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logdet, float* z_nchw,
+                      float* weight_scale, int batch, int training, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, training ? 1 : 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(!p->single, "flow entry points need a plan made by rnvp_plan_create");
+  const rnvp_config& cf = p->cfg;
+  const int L = cf.num_scales;
+  p->saved_batch = -1;
+  p->saved_coupling = -1;
+  RNVP_TRY(zero_pass(c, false));
+  RNVP_TRY(clear_padding(c));
+  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  if (weight_scale) {
+    RNVP_TRY(k_sumsq(p->d_segs, p->nsegs, c.ws_acc(), c.st));
+    RNVP_TRY(k_sumsq_finish(c.ws_acc(), weight_scale, c.st));
+  }
+  FlowBufs f = flow_bufs(c);
+  RNVP_TRY(k_nchw_to_nhwc(x_nchw, f.in_ckbd[1], batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  const float* cur = f.in_ckbd[1];
+  int ci = 0, chan = cf.channels, size = cf.image_size, flip = 0;
+  auto run_group = [&](int n) -> int {
+    for (int i = 0; i < n; ++i, ++ci) {
+      CplAct A = cpl_act(p, p->cpl[ci], batch, c.mode);
+      float* y = training ? c.act(ci, A.y) : f.T[flip ^= 1];
+      RNVP_TRY(coupling_forward(c, ci, cur, y, nullptr, training));
+      cur = y;
+    }
+    return RNVP_OK;
+  };
+  for (int s = 1; s < L; ++s) {
+    RNVP_TRY(run_group(3));
+    RNVP_TRY(k_permute(PERM_SQUEEZE, cur, nullptr, nullptr, nullptr, nullptr, f.in_chan[s], nullptr, nullptr, batch,
+                       size / 2, chan, c.st));
+    cur = f.in_chan[s];
+    RNVP_TRY(run_group(3));
+    // undo_squeeze o factor_out is a channel permutation at the squeezed resolution
+    RNVP_TRY(k_permute(PERM_UNSQ_FACTOR, nullptr, cur, nullptr, nullptr, nullptr, nullptr, f.in_ckbd[s + 1], f.off[s],
+                       batch, size / 2, chan, c.st));
+    RNVP_TRY(k_prior_ll(f.off[s], batch, (int)(f.n[s] / 2 / batch), cf.prior_loc, cf.prior_scale, c.prior_acc(), c.st));
+    cur = f.in_ckbd[s + 1];
+    chan *= 2; size /= 2;
+  }
+  RNVP_TRY(run_group(4));
+  RNVP_TRY(k_prior_ll(cur, batch, (int)(f.n[L] / batch), cf.prior_loc, cf.prior_scale, c.prior_acc(), c.st));
+  RNVP_TRY(k_finalize_ll(c.logdet_acc(), c.prior_acc(), ll, logdet, batch, c.st));
+  if (z_nchw) {
+    // z = restore(...restore(z_L, off_{L-1})..., off_1)      flow_realnvp.py:316-325
+    const float* t = cur;
+    int ch = chan, sz = size, k = 0;
+    for (int s = L - 1; s >= 1; --s) {
+      float* dst = f.G[k ^= 1];
+      RNVP_TRY(k_permute(PERM_RESTORE, nullptr, nullptr, t, f.off[s], dst, nullptr, nullptr, nullptr, batch, sz,
+                         ch / 2, c.st));
+      t = dst;
+      ch /= 2; sz *= 2;
+    }
+    RNVP_TRY(k_nhwc_to_nchw(t, z_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  }
+  if (training) p->saved_batch = batch;
+  return RNVP_OK;
+}
+
+int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scale, float* dx_nchw, int batch, void* ws,
+                       size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, 1, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(!p->single, "flow entry points need a plan made by rnvp_plan_create");
+  if (p->saved_batch != batch) {
+    set_error("rnvp_flow_backward: no matching training forward (saved batch %d, got %d)", p->saved_batch, batch);
+    return RNVP_ERR_STATE;
+  }
+  const rnvp_config& cf = p->cfg;
+  const int L = cf.num_scales;
+  RNVP_TRY(zero_pass(c, true));
+  if (dweight_scale != nullptr) RNVP_TRY(k_sumsq_bwd(p->d_segs, p->nsegs, dweight_scale, c.st));
+  FlowBufs f = flow_bufs(c);
+  int ci = (int)p->cpl.size() - 1;
+  int chan = cf.channels << (L - 1), size = cf.image_size >> (L - 1), k = 0;
+  // gradient of the prior term wrt the final latent block
+  {
+    const CouplingDesc& last = p->cpl[ci];
+    CplAct A = cpl_act(p, last, batch, 1);
+    RNVP_TRY(k_prior_grad(c.act(ci, A.y), dll, f.G[0], 0, batch, (int)(f.n[L] / batch), cf.prior_loc,
+                          cf.prior_scale, c.st));
+  }
+  float* dcur = f.G[0];
+  auto run_group = [&](int n) -> int {
+    for (int i = 0; i < n; ++i, --ci) {
+      float* dx = f.G[k ^= 1];
+      RNVP_TRY(coupling_backward(c, ci, dcur, dll, dx));
+      dcur = dx;
+    }
+    return RNVP_OK;
+  };
+  RNVP_TRY(run_group(4));
+  for (int s = L - 1; s >= 1; --s) {
+    chan /= 2; size *= 2;                     // (chan,size) of the tensor entering scale s
+    // (on, off) = perm(sq): d_sq = perm^-1(d_on, d_off); d_off is the prior gradient of off_s
+    RNVP_TRY(k_prior_grad(f.off[s], dll, f.G[2], 0, batch, (int)(f.n[s] / 2 / batch), cf.prior_loc, cf.prior_scale, c.st));
+    float* dsq = f.G[k ^= 1];
+    RNVP_TRY(k_permute(PERM_FACTOR_SQ, nullptr, nullptr, dcur, f.G[2], nullptr, dsq, nullptr, nullptr, batch,
+                       size / 2, chan, c.st));
+    dcur = dsq;
+    RNVP_TRY(run_group(3));
+    float* dhi = f.G[k ^= 1];
+    RNVP_TRY(k_permute(PERM_UNDO_SQUEEZE, nullptr, dcur, nullptr, nullptr, dhi, nullptr, nullptr, nullptr, batch,
+                       size / 2, chan, c.st));
+    dcur = dhi;
+    RNVP_TRY(run_group(3));
+  }
+  if (dx_nchw) RNVP_TRY(k_nhwc_to_nchw(dcur, dx_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  p->saved_batch = -1;
+  return RNVP_OK;
+}
+
+int rnvp_flow_inverse(rnvp_plan* p, const float* z_nchw, float* x_nchw, int batch, int training, void* ws,
+                      size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(!p->single, "flow entry points need a plan made by rnvp_plan_create");
+  const rnvp_config& cf = p->cfg;
+  const int L = cf.num_scales;
+  p->saved_batch = -1;
+  p->saved_coupling = -1;
+  RNVP_TRY(zero_pass(c, false));
+  RNVP_TRY(clear_padding(c));
+  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  FlowBufs f = flow_bufs(c);
+  // factor_out chain (flow_realnvp.py:197-200): in_ckbd[s+1], off[s] = factor_out(in_ckbd[s])
+  RNVP_TRY(k_nchw_to_nhwc(z_nchw, f.in_ckbd[1], batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  int chan = cf.channels, size = cf.image_size;
+  for (int s = 1; s < L; ++s) {
+    RNVP_TRY(k_permute(PERM_FACTOR_OUT, f.in_ckbd[s], nullptr, nullptr, nullptr, nullptr, nullptr, f.in_ckbd[s + 1],
+                       f.off[s], batch, size / 2, chan, c.st));
+    chan *= 2; size /= 2;
+  }
+  const float* cur = f.in_ckbd[L];
+  int ci = (int)p->cpl.size() - 1, flip = 0;
+  auto run_group = [&](int n) -> int {
+    for (int i = 0; i < n; ++i, --ci) {
+      float* x = f.T[flip ^= 1];
+      RNVP_TRY(coupling_inverse(c, ci, cur, x, training));
+      cur = x;
+    }
+    return RNVP_OK;
+  };
+  RNVP_TRY(run_group(4));
+  for (int s = L - 1; s >= 1; --s) {
+    chan /= 2; size *= 2;
+    // restore o squeeze: channel permutation at the low resolution
+    float* sq = f.in_chan[s];
+    RNVP_TRY(k_permute(PERM_FACTOR_SQ, nullptr, nullptr, cur, f.off[s], nullptr, sq, nullptr, nullptr, batch, size / 2,
+                       chan, c.st));
+    cur = sq;
+    RNVP_TRY(run_group(3));
+    float* hi = f.in_ckbd[s];
+    RNVP_TRY(k_permute(PERM_UNDO_SQUEEZE, nullptr, cur, nullptr, nullptr, hi, nullptr, nullptr, nullptr, batch,
+                       size / 2, chan, c.st));
+    cur = hi;
+    RNVP_TRY(run_group(3));
+  }
+  RNVP_TRY(k_nhwc_to_nchw(cur, x_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  return RNVP_OK;
+}
+
+// ---- one coupling, NCHW boundary -------------------------------------------------------
+int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nchw, float* logJ_nchw, int batch,
+                          int training, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, training ? 1 : 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(ci >= 0 && ci < (int)p->cpl.size(), "coupling index %d out of range", ci);
+  const CouplingDesc& d = p->cpl[ci];
+  p->saved_batch = -1;
+  p->saved_coupling = -1;
+  RNVP_TRY(zero_pass(c, false));
+  RNVP_TRY(clear_padding(c));
+  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  FlowBufs f = flow_bufs(c);
+  RNVP_TRY(k_nchw_to_nhwc(x_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
+  RNVP_TRY(coupling_forward(c, ci, f.T[0], f.T[1], logJ_nchw ? f.G[0] : nullptr, training));
+  RNVP_TRY(k_nhwc_to_nchw(f.T[1], y_nchw, batch, d.C, d.S, d.S, c.st));
+  if (logJ_nchw) RNVP_TRY(k_nhwc_to_nchw(f.G[0], logJ_nchw, batch, d.C, d.S, d.S, c.st));
+  if (training) { p->saved_coupling = ci; p->saved_batch = batch; }
+  return RNVP_OK;
+}
+
+int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nchw, int batch, int training,
+                          void* ws, size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(ci >= 0 && ci < (int)p->cpl.size(), "coupling index %d out of range", ci);
+  const CouplingDesc& d = p->cpl[ci];
+  p->saved_batch = -1;
+  p->saved_coupling = -1;
+  RNVP_TRY(zero_pass(c, false));
+  RNVP_TRY(clear_padding(c));
+  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  FlowBufs f = flow_bufs(c);
+  RNVP_TRY(k_nchw_to_nhwc(y_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
+  RNVP_TRY(coupling_inverse(c, ci, f.T[0], f.T[1], training));
+  RNVP_TRY(k_nhwc_to_nchw(f.T[1], x_nchw, batch, d.C, d.S, d.S, c.st));
+  return RNVP_OK;
+}
+
+int rnvp_coupling_backward(rnvp_plan* p, int ci, const float* dy_nchw, const float* dlogJ_nchw, float* dx_nchw,
+                           int batch, void* ws, size_t ws_bytes, void* stream) {
+  Ctx c;
+  RNVP_TRY(make_ctx(p, batch, 1, ws, ws_bytes, stream, &c));
+  if (p->saved_coupling != ci || p->saved_batch != batch) {
+    set_error("rnvp_coupling_backward: no matching training forward of coupling %d at batch %d", ci, batch);
+    return RNVP_ERR_STATE;
+  }
+  const CouplingDesc& d = p->cpl[ci];
+  RNVP_TRY(zero_pass(c, true));
+  FlowBufs f = flow_bufs(c);
+  RNVP_TRY(k_nchw_to_nhwc(dy_nchw, f.G[0], batch, d.C, d.S, d.S, c.st));
+  RNVP_TRY(k_gather_first(dlogJ_nchw, f.dll, batch, d.C * d.S * d.S, c.st));
+  RNVP_TRY(coupling_backward(c, ci, f.G[0], f.dll, f.G[1]));
+  RNVP_TRY(k_nhwc_to_nchw(f.G[1], dx_nchw, batch, d.C, d.S, d.S, c.st));
+  p->saved_coupling = -1;
+  p->saved_batch = -1;
+  return RNVP_OK;
+}
+
+// ---- logit, layout, building blocks ------------------------------------------------------
+int rnvp_logit_forward(const float* x, const float* noise, float* y, float* logdet, int batch, int n,
+                       float constraint, uint64_t seed, uint64_t offset, void* stream) {
+  return k_logit_fwd(x, nullptr, noise, y, logdet, batch, n, constraint, seed, offset, (cudaStream_t)stream);
+}
+int rnvp_logit_forward_u8(const uint8_t* x, const float* noise, float* y, float* logdet, int batch, int n,
+                          float constraint, uint64_t seed, uint64_t offset, void* stream) {
+  return k_logit_fwd(nullptr, x, noise, y, logdet, batch, n, constraint, seed, offset, (cudaStream_t)stream);
+}
+int rnvp_logit_inverse(const float* y, float* x, size_t n, float constraint, void* stream) {
+  return k_logit_inv(y, x, n, constraint, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace {
+// NCHW wrappers around the NHWC permute kernel need two scratch tensors; the layout entry points
+// are API-completeness paths (the flow never calls them), so they allocate stream-ordered scratch.
+struct Scratch {
+  float* p = nullptr;
+  cudaStream_t st;
+  int alloc(size_t floats, cudaStream_t s) {
+    st = s;
+    RNVP_CUDA(cudaMallocAsync(&p, floats * 4, s));
+    return RNVP_OK;
+  }
+  ~Scratch() { if (p) cudaFreeAsync(p, st); }
+};
+}  // namespace
+
+extern "C" {
+
+int rnvp_squeeze(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  RNVP_REQUIRE(H == W && H % 2 == 0, "squeeze needs a square, even-sized input");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)B * C * H * W;
+  Scratch s;
+  RNVP_TRY(s.alloc(2 * n, st));
+  RNVP_TRY(k_nchw_to_nhwc(x, s.p, B, C, H, W, st));
+  RNVP_TRY(k_permute(PERM_SQUEEZE, s.p, nullptr, nullptr, nullptr, nullptr, s.p + n, nullptr, nullptr, B, H / 2, C, st));
+  return k_nhwc_to_nchw(s.p + n, y, B, 4 * C, H / 2, W / 2, st);
+}
+int rnvp_undo_squeeze(const float* x, float* y, int B, int C, int H, int W, void* stream) {
+  RNVP_REQUIRE(H == W && C % 4 == 0, "undo_squeeze needs a square input with 4k channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)B * C * H * W;
+  Scratch s;
+  RNVP_TRY(s.alloc(2 * n, st));
+  RNVP_TRY(k_nchw_to_nhwc(x, s.p, B, C, H, W, st));
+  RNVP_TRY(k_permute(PERM_UNDO_SQUEEZE, nullptr, s.p, nullptr, nullptr, s.p + n, nullptr, nullptr, nullptr, B, H, C / 4, st));
+  return k_nhwc_to_nchw(s.p + n, y, B, C / 4, H * 2, W * 2, st);
+}
+int rnvp_factor_out(const float* x, float* on, float* off, int B, int C, int H, int W, void* stream) {
+  RNVP_REQUIRE(H == W && H % 2 == 0, "factor_out needs a square, even-sized input");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)B * C * H * W;
+  Scratch s;
+  RNVP_TRY(s.alloc(2 * n, st));
+  RNVP_TRY(k_nchw_to_nhwc(x, s.p, B, C, H, W, st));
+  RNVP_TRY(k_permute(PERM_FACTOR_OUT, s.p, nullptr, nullptr, nullptr, nullptr, nullptr, s.p + n, s.p + n + n / 2, B,
+                     H / 2, C, st));
+  RNVP_TRY(k_nhwc_to_nchw(s.p + n, on, B, 2 * C, H / 2, W / 2, st));
+  return k_nhwc_to_nchw(s.p + n + n / 2, off, B, 2 * C, H / 2, W / 2, st);
+}
+int rnvp_restore(const float* on, const float* off, float* x, int B, int C, int H, int W, void* stream) {
+  // on/off are (B,C,H,W); x is (B,C/2,2H,2W)
+  RNVP_REQUIRE(H == W && C % 2 == 0, "restore needs square inputs with an even channel count");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)B * C * H * W;
+  Scratch s;
+  RNVP_TRY(s.alloc(4 * n, st));
+  RNVP_TRY(k_nchw_to_nhwc(on, s.p, B, C, H, W, st));
+  RNVP_TRY(k_nchw_to_nhwc(off, s.p + n, B, C, H, W, st));
+  RNVP_TRY(k_permute(PERM_RESTORE, nullptr, nullptr, s.p, s.p + n, s.p + 2 * n, nullptr, nullptr, nullptr, B, H, C / 2, st));
+  return k_nhwc_to_nchw(s.p + 2 * n, x, B, C / 2, 2 * H, 2 * W, st);
+}
+
+int rnvp_weightnorm_forward(const float* v, const float* g, float* wf, float* wb, int cout, int cin, int ksize,
+                            void* stream) {
+  RNVP_REQUIRE(wf && wb, "both operand layouts are produced; pass two buffers");
+  cudaStream_t st = (cudaStream_t)stream;
+  WnJob j{};
+  j.v = v; j.g = g;
+  j.cout = cout; j.cin = cin; j.taps = ksize * ksize;
+  j.npad_f = pad_to(cout, 16); j.kpad_f = pad_to(cin, 32); j.npad_b = pad_to(cin, 16); j.kpad_b = pad_to(cout, 32);
+  j.wf_off = 0;
+  j.wb_off = (size_t)(wb - wf);               // relative to wf as the arena base
+  RNVP_REQUIRE(wb > wf, "wb must follow wf in memory (single allocation)");
+  Scratch s;
+  RNVP_TRY(s.alloc(sizeof(WnJob) / 4 + 1, st));
+  RNVP_CUDA(cudaMemcpyAsync(s.p, &j, sizeof(j), cudaMemcpyHostToDevice, st));
+  RNVP_CUDA(cudaStreamSynchronize(st));
+  return k_weightnorm_fwd(reinterpret_cast<WnJob*>(s.p), 1, cout, wf, st);
+}
+int rnvp_weightnorm_backward(const float* v, const float* g, const float* dwf, float* dv, float* dg, int cout,
+                             int cin, int ksize, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  WnJob j{};
+  j.v = v; j.g = g; j.dv = dv; j.dg = dg;
+  j.cout = cout; j.cin = cin; j.taps = ksize * ksize;
+  j.npad_f = pad_to(cout, 16); j.kpad_f = pad_to(cin, 32); j.npad_b = pad_to(cin, 16); j.kpad_b = pad_to(cout, 32);
+  j.dw_off = 0;
+  Scratch s;
+  RNVP_TRY(s.alloc(sizeof(WnJob) / 4 + 1, st));
+  RNVP_CUDA(cudaMemcpyAsync(s.p, &j, sizeof(j), cudaMemcpyHostToDevice, st));
+  RNVP_CUDA(cudaStreamSynchronize(st));
+  return k_weightnorm_bwd(reinterpret_cast<WnJob*>(s.p), 1, cout, nullptr, dwf, st);
+}
+
+int rnvp_conv_forward(const float* x, const float* wf, const float* bias, const float* res, float* y, double* stats,
+                      int B, int S, int kpad, int n, int npad, int ksize, int ldy, int math, void* stream) {
+  ConvArgs a{};
+  a.x = x; a.w = wf; a.bias = bias; a.res = res; a.y = y; a.stats = stats;
+  a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.ldy = ldy;
+  return math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, (cudaStream_t)stream) : k_conv_fwd_fp32(a, (cudaStream_t)stream);
+}
+int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias, int B, int S, int kpad, int n,
+                    int npad, int ksize, int lddy, int math, void* stream) {
+  WgradArgs a{};
+  a.x = x; a.dy = dy; a.dw = dwf; a.dbias = dbias;
+  a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.lddy = lddy;
+  return math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, (cudaStream_t)stream) : k_conv_wgrad_fp32(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"
+
+namespace rnvp {
+void** plan_comm_slot(rnvp_plan* p) { return &p->comm; }
+void plan_set_ranks(rnvp_plan* p, int rank, int world) { p->rank = rank; p->world = world; }
+int plan_world(const rnvp_plan* p) { return p->world; }
+}  // namespace rnvp

@@ -1,0 +1,198 @@
+/*
+ * rnvp.h -- C-ABI of the B200-native RealNVP coupling-stack hot path.
+ *
+ * The reference (alisher-turubayev/dl-normalizing-flows) has no FFI: its
+ * boundary is the Python class API in flow_realnvp.py / modules_realnvp.py /
+ * utils.py, all of whose arithmetic runs inside torch.  This header is the
+ * boundary a maintainer binds (ctypes) to move that
+ * arithmetic onto sm_100a kernels.  Each entry point names the reference code
+ * it replaces (file:line into the reference tree).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative rnvp_status otherwise;
+ *     rnvp_last_error() gives the message for the calling thread.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*; nothing is cached per thread,
+ *     so autograd's backward thread may call in (SURVEY.md 8b "Threading").
+ *   - the library allocates no persistent device memory except the small
+ *     per-plan tables created by rnvp_plan_create / rnvp_plan_bind; all
+ *     activations, saved tensors and scratch live in a caller-owned workspace.
+ *   - activations inside the library are NHWC fp32 with the channel stride of
+ *     conv operands padded to a multiple of 32; the public entry points take and
+ *     return the reference's NCHW fp32 tensors.
+ */
+#ifndef RNVP_H_
+#define RNVP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  RNVP_OK = 0,
+  RNVP_ERR_INVALID = -1,     /* bad argument / unsupported configuration   */
+  RNVP_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed        */
+  RNVP_ERR_WORKSPACE = -3,   /* workspace too small                        */
+  RNVP_ERR_STATE = -4,       /* call order violated (e.g. backward w/o fwd)*/
+  RNVP_ERR_NCCL = -5
+} rnvp_status;
+
+/* conv arithmetic tier (SURVEY.md 7 "precision tiers") */
+typedef enum {
+  RNVP_MATH_FP32 = 0,        /* CUDA-core fp32 FMA implicit GEMM (1e-5 tier, reconstruction gate) */
+  RNVP_MATH_TF32 = 1         /* tcgen05 kind::tf32, fp32 accumulate in TMEM (1e-3 tier, throughput) */
+} rnvp_math;
+
+/* RealNVP(channels, image_size, prior, hps): flow_realnvp.py:36-95, utils.py:78-93.
+ * num_scales = 5 reproduces the in-tree model; other values give the same
+ * doubling rule truncated (BASELINE config 3).                              */
+typedef struct {
+  int32_t channels;
+  int32_t image_size;
+  int32_t base_dim;
+  int32_t res_blocks;
+  int32_t num_scales;
+  float prior_loc;           /* torch.distributions.Normal(loc, scale), train.py:109 */
+  float prior_scale;
+} rnvp_config;
+
+typedef struct rnvp_plan rnvp_plan;
+
+const char* rnvp_last_error(void);
+const char* rnvp_version(void);
+int rnvp_device_ok(void);                      /* 0 when cuda:current is sm_100 */
+
+/* ---- plan ------------------------------------------------------------- */
+int rnvp_plan_create(const rnvp_config* cfg, rnvp_plan** out);
+/* a plan holding ONE stand-alone coupling module, as constructed by
+ * CheckerboardAffineCoupling(in_out_dim=C, mid_dim=D, size=S, mask_config, hps)   (kind 0,
+ * modules_realnvp.py:240) or ChannelwiseAffineCoupling(in_out_dim=C, mid_dim=D, mask_config, hps)
+ * (kind 1, modules_realnvp.py:305); only the rnvp_coupling_* entry points accept it.           */
+int rnvp_plan_create_single(int kind, int C, int S, int D, int mask_cfg, int res_blocks, rnvp_plan** out);
+int rnvp_plan_destroy(rnvp_plan* plan);
+int rnvp_plan_num_couplings(const rnvp_plan* plan);
+/* number of pointer slots per coupling in the parameter table (see
+ * rnvp_plan_slot_name) and in total                                        */
+int rnvp_plan_slots_per_coupling(const rnvp_plan* plan);
+/* name of slot `i` relative to its coupling module, e.g.
+ * "block.1.core_block.0.res_block.3.conv.weight_v" -- the reference's
+ * state-dict key suffix.  Returns NULL when out of range.    */
+const char* rnvp_plan_slot_name(const rnvp_plan* plan, int slot);
+/* coupling `i`: name ("s1_ckbd.0"), kind (0 ckbd / 1 chan), C, S, D, mask cfg */
+int rnvp_plan_coupling_info(const rnvp_plan* plan, int i, char* name, int name_len,
+                            int* kind, int* C, int* S, int* D, int* mask_cfg);
+
+/* Bind parameter / gradient device pointers.  `params` and `grads` are HOST
+ * arrays of num_couplings*slots_per_coupling device pointers; grads entries
+ * are NULL for buffers and frozen parameters (weight_g of scale=False convs,
+ * modules_realnvp.py:57-59).  Re-bind whenever a pointer changes.  Not
+ * capturable in a CUDA graph (it uploads tables).                          */
+int rnvp_plan_bind(rnvp_plan* plan, void* const* params_host, void* const* grads_host, void* stream);
+
+/* bytes of workspace the calls below need for batch B.
+ * mode: 0 = inference forward / inverse, 1 = training forward + backward   */
+size_t rnvp_plan_workspace_bytes(const rnvp_plan* plan, int batch, int mode);
+
+int rnvp_plan_set_math(rnvp_plan* plan, int math /* rnvp_math */);
+
+/* ---- the flow (flow_realnvp.py:196-370) -------------------------------- */
+/* log_prob / forward (flow_realnvp.py:329-340, 354-370).
+ *   x_nchw       (B,C,H,W) logit-space input
+ *   ll           (B)  log prior + log det                       [out]
+ *   logdet       (B)  log det only, may be NULL                 [out]
+ *   z_nchw       (B,C,H,W) latent, may be NULL                  [out]
+ *   weight_scale (1)  sum p^2 over trainable weight_g / scale, may be NULL [out]
+ *   training     1: batch statistics, running stats updated, tensors saved in
+ *                   the workspace for rnvp_flow_backward; 0: running statistics */
+int rnvp_flow_forward(rnvp_plan* plan, const float* x_nchw, float* ll, float* logdet, float* z_nchw,
+                      float* weight_scale, int batch, int training,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* backward of rnvp_flow_forward(training=1) (autograd of flow_realnvp.py:252-340
+ * and of the modules).  dll (B) is dLoss/dll, dweight_scale a
+ * DEVICE scalar holding dLoss/dweight_scale (NULL = 0).  Parameter gradients are ADDED
+ * into the bound grads; dx_nchw (may be NULL) receives dLoss/dx.            */
+int rnvp_flow_backward(rnvp_plan* plan, const float* dll, const float* dweight_scale, float* dx_nchw,
+                       int batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/* g: z -> x (flow_realnvp.py:196-249).  training selects batch vs running
+ * statistics for in_bn exactly like nn.BatchNorm2d; the un-normalisation of
+ * out_bn always uses running statistics (modules_realnvp.py:285-291).       */
+int rnvp_flow_inverse(rnvp_plan* plan, const float* z_nchw, float* x_nchw, int batch, int training,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- one coupling (modules_realnvp.py:264-302, 324-370) ----------------- */
+/* forward(x, reverse=False): y and the full log_diag_J tensor (both NCHW,
+ * (B,C,S,S)); logdet (B) optional per-sample sum.  With training=1 the
+ * tensors needed by rnvp_coupling_backward stay in the workspace.            */
+int rnvp_coupling_forward(rnvp_plan* plan, int coupling, const float* x_nchw, float* y_nchw,
+                          float* logJ_nchw, int batch, int training,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* forward(x, reverse=True) */
+int rnvp_coupling_inverse(rnvp_plan* plan, int coupling, const float* y_nchw, float* x_nchw,
+                          int batch, int training,
+                          void* workspace, size_t workspace_bytes, void* stream);
+/* VJP of rnvp_coupling_forward(training=1): dy, dlogJ (B,C,S,S) NCHW upstream
+ * grads -> dx; parameter grads are added into the bound grads.
+ * dlogJ must be constant within a sample (it is dLoss/dll broadcast) -- the
+ * per-sample value is read from element 0 of each sample.                    */
+int rnvp_coupling_backward(rnvp_plan* plan, int coupling, const float* dy_nchw, const float* dlogJ_nchw,
+                           float* dx_nchw, int batch,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- logit dequantisation (utils.py:33-72) ------------------------------ */
+/* forward: x in [0,1] (fp32, n_per_sample = C*H*W), noise in [0,1) or NULL
+ * (then Philox(seed, offset) noise is drawn in-kernel, utils.py:47);
+ * y and per-sample log-det out.                                             */
+int rnvp_logit_forward(const float* x, const float* noise, float* y, float* logdet,
+                       int batch, int n_per_sample, float constraint,
+                       uint64_t seed, uint64_t offset, void* stream);
+/* same from uint8 pixels (value/255 is what ToTensor yields, train.py:69) */
+int rnvp_logit_forward_u8(const uint8_t* x, const float* noise, float* y, float* logdet,
+                          int batch, int n_per_sample, float constraint,
+                          uint64_t seed, uint64_t offset, void* stream);
+/* reverse=True branch, utils.py:34-42 */
+int rnvp_logit_inverse(const float* y, float* x, size_t n, float constraint, void* stream);
+
+/* ---- layout transforms (flow_realnvp.py:121-193), NCHW in / NCHW out ---- */
+int rnvp_squeeze(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int rnvp_undo_squeeze(const float* x, float* y, int B, int C, int H, int W, void* stream);
+int rnvp_factor_out(const float* x, float* on, float* off, int B, int C, int H, int W, void* stream);
+int rnvp_restore(const float* on, const float* off, float* x, int B, int C, int H, int W, void* stream);
+
+/* ---- building blocks exposed for per-op parity tests --------------------- */
+/* w = g * v / ||v|| (modules_realnvp.py:53-56) into the padded GEMM layouts:
+ *   wf [taps][pad16(Cout)][pad32(Cin)]   forward operand
+ *   wb [taps][pad16(Cin)][pad32(Cout)]   dgrad operand (taps flipped, transposed); may be NULL */
+int rnvp_weightnorm_forward(const float* v, const float* g, float* wf, float* wb,
+                            int cout, int cin, int ksize, void* stream);
+/* dwf (same layout as wf) -> dv (+=), dg (+=, may be NULL when g is frozen) */
+int rnvp_weightnorm_backward(const float* v, const float* g, const float* dwf, float* dv, float* dg,
+                             int cout, int cin, int ksize, void* stream);
+/* stride-1 "same" conv as implicit GEMM over NHWC:
+ *   y[p, n] = sum_tap sum_k x[p + tap, k] * wf[tap][n][k] (+ bias[n]) (+ res[p, n])
+ * x [B,S,S,kpad], wf [taps][npad][kpad], y/res row stride ldy.  stats (2*n
+ * doubles, optional) accumulates per-channel sum and sum of squares of y.    */
+int rnvp_conv_forward(const float* x, const float* wf, const float* bias, const float* res, float* y,
+                      double* stats, int B, int S, int kpad, int n, int npad, int ksize, int ldy,
+                      int math, void* stream);
+/* dwf[tap][n][k] += sum_p dy[p, n] * x[p + tap, k];  dbias[n] += sum_p dy[p, n] (optional) */
+int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias,
+                    int B, int S, int kpad, int n, int npad, int ksize, int lddy,
+                    int math, void* stream);
+
+/* ---- data parallel (absent from the reference) ------------- */
+/* 128-byte NCCL unique id, created on rank 0 and shipped by the caller      */
+int rnvp_dp_unique_id(void* id128_host);
+int rnvp_dp_init(rnvp_plan* plan, const void* id128_host, int rank, int world);
+int rnvp_dp_finalize(rnvp_plan* plan);
+/* sum-all-reduce `n` floats in place on `stream` (gradient buckets)         */
+int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RNVP_H_ */

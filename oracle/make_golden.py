@@ -246,6 +246,12 @@ def misc_case(ref_flow, ref_utils, out_dir):
     assert torch.equal(on, on_o) and torch.equal(off, off_o)
     assert torch.equal(m.restore(on, off, m.order_matrix_1), O.restore(on, off))
     fix["layout"] = {"t": t, "squeeze": sq, "on": on, "off": off}
+    # initialisation under a seed (main.py:58-59 seeds torch; default fixed_seed 999)
+    torch.manual_seed(999)
+    hps2 = ref_utils.Hyperparameters(4, 2, True, True, True, True)
+    m2 = ref_flow.RealNVP(3, 32, prior, hps2)
+    fix["init_sha256_seed999_3x32_b4_r2"] = state_checksum(m2.state_dict())
+    fix["param_names_3x32_b4_r2"] = [(n, bool(p.requires_grad)) for n, p in m2.named_parameters()]
     torch.save(fix, os.path.join(out_dir, "misc.pt"))
     print("[misc] ok")
 

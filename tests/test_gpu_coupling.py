@@ -1,0 +1,60 @@
+"""-m gpu: stand-alone coupling modules vs the reference's outputs (tests/golden/couplings.pt)."""
+import os
+
+import pytest
+import torch
+
+import realnvp_oracle as O
+from _util import rel, sha
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _build(pkg, case, math):
+    kind, C, S, D, cfg, R = case["kind"], case["C"], case["S"], case["D"], case["cfg"], case["R"]
+    hps = pkg.Hyperparameters(8, R, True, True, True, True)
+    if kind == "ckbd":
+        mod = pkg.CheckerboardAffineCoupling(C, D, S, float(cfg), hps)
+    else:
+        mod = pkg.ChannelwiseAffineCoupling(C, D, float(cfg), hps)
+    st = O.random_state_from_shapes(O.coupling_state_shapes("", kind, C, D, R), seed=case["seed"])
+    assert sha(st) == case["state_sha256"]
+    mod.load_state_dict(st, strict=True)
+    pkg.set_default_math(math)
+    return mod.to(DEV), st
+
+
+@pytest.mark.parametrize("math,tol", [("fp32", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_coupling_forward_inverse_vjp(pkg, golden_dir, math, tol, mode):
+    fix = torch.load(os.path.join(golden_dir, "couplings.pt"))
+    try:
+        for tag, case in fix.items():
+            mod, st = _build(pkg, case, math)
+            mod.train(mode == "train")
+            ref = case[mode]
+            x = case["x"].to(DEV).requires_grad_(True)
+            if mode == "train":
+                y, J = mod(x)
+                (y * case["gy"].to(DEV)).sum().add((J * case["gJ"].to(DEV)).sum()).backward()
+                assert rel(y, ref["y"]) < tol and rel(J, ref["J"]) < tol, (tag, rel(y, ref["y"]), rel(J, ref["J"]))
+                assert rel(x.grad, ref["gx"]) < 20 * tol, (tag, rel(x.grad, ref["gx"]))
+                gmax = max(float(g.abs().max()) for g in ref["grads"].values())
+                for k, g in ref["grads"].items():
+                    got = dict(mod.named_parameters())[k].grad
+                    assert got is not None, k
+                    err = float((got.cpu() - g).abs().max()) / max(float(g.abs().max()), 1e-3 * gmax)
+                    assert err < 40 * tol, (tag, k, err)
+                for k, v in ref["stats_after"].items():
+                    assert torch.allclose(mod.state_dict()[k].cpu(), v, rtol=20 * tol, atol=tol), (tag, k)
+            else:
+                with torch.no_grad():
+                    y, J = mod(x)
+                assert rel(y, ref["y"]) < tol and rel(J, ref["J"]) < tol, (tag, rel(y, ref["y"]))
+            mod.load_state_dict(st, strict=True)
+            with torch.no_grad():
+                xi, _ = mod(case["x"].to(DEV), reverse=True)
+            assert rel(xi, ref["inv"]) < 5 * tol, (tag, rel(xi, ref["inv"]))
+    finally:
+        pkg.set_default_math("tf32")

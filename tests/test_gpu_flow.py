@@ -1,0 +1,196 @@
+"""-m gpu: the whole multi-scale stack through the drop-in RealNVP vs the reference's outputs."""
+import os
+
+import pytest
+import torch
+
+import realnvp_oracle as O
+from _util import compare_grads, rel, sha
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build(pkg, c, state, math):
+    prior = torch.distributions.Normal(torch.tensor(0., device=DEV), torch.tensor(1., device=DEV), validate_args=False)
+    hps = pkg.Hyperparameters(c["base_dim"], c["res_blocks"], True, True, True, True)
+    kw = {} if c.get("num_scales", 5) == 5 else {"num_scales": c["num_scales"]}
+    m = pkg.RealNVP(c["channels"], c["image"], prior, hps, **kw)
+    m.load_state_dict(state, strict=True)
+    m = m.to(DEV)
+    m.set_math(math)
+    return m
+
+
+# tolerances: fp32 tier 1e-5 on log-lik (north star), tf32 tier 1e-3
+TIERS = [("fp32", 1e-5, 5e-4, 2e-2), ("tf32", 1e-3, 0.3, 0.1)]
+
+
+@pytest.mark.parametrize("math,ll_tol,z_tol,g_tol", TIERS)
+@pytest.mark.parametrize("name", ["tiny_32px_b4", "small_64px_b2"])
+def test_golden_model(pkg, golden_dir, name, math, ll_tol, z_tol, g_tol):
+    fix = torch.load(os.path.join(golden_dir, name + ".pt"))
+    c = fix["config"]
+    st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
+    assert sha(st0) == fix["state_sha256"]
+    x = fix["x"].to(DEV)
+    # ---- train-mode forward + backward, as train.py:191-198 drives it ---------------------
+    m = build(pkg, c, st0, math)
+    m.train()
+    ll, ws = m(x)
+    assert ll.shape == (c["B"],) and ws.dim() == 0
+    assert rel(ll, fix["train_ll"]) < ll_tol, rel(ll, fix["train_ll"])
+    assert rel(ws, fix["train_ws"]) < 1e-6
+    loss = -(ll).mean() + 5e-5 * ws
+    loss.backward()
+    got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+    assert set(got) == set(fix["train_grads"])
+    grel, worst, wk = compare_grads(got, fix["train_grads"], fix["train_grad_norms"])
+    assert grel < g_tol, (grel, worst, wk)
+    if math == "fp32":
+        assert worst < 0.05, (worst, wk)
+    sd = m.state_dict()
+    for k, v in fix["state_after_train"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert torch.allclose(sd[k].cpu(), v, rtol=max(1e-4, 10 * ll_tol), atol=max(1e-5, ll_tol)), k
+    # ---- z and the full log_diag_J through f() ------------------------------------------------
+    m2 = build(pkg, c, st0, math)
+    m2.train()
+    with torch.no_grad():
+        z, J = m2.f(x)
+    assert rel(J.sum((1, 2, 3)), fix["train_J"].sum((1, 2, 3))) < ll_tol
+    if math == "fp32":
+        assert rel(z, fix["train_z"]) < z_tol and rel(J, fix["train_J"]) < z_tol
+    m3 = build(pkg, c, st0, math)
+    m3.train()
+    z3, ld3, ll3 = m3.latent(x)
+    assert rel(ld3, fix["train_J"].sum((1, 2, 3))) < ll_tol
+    if math == "fp32":
+        assert rel(z3, fix["train_z"]) < z_tol
+    # ---- eval mode --------------------------------------------------------------------------------
+    m4 = build(pkg, c, st0, math)
+    m4.eval()
+    with torch.no_grad():
+        lle, _ = m4(x)
+        assert rel(lle, fix["eval_ll"]) < ll_tol, rel(lle, fix["eval_ll"])
+        xs = m4.g(fix["z_sample"].to(DEV))
+        if math == "fp32":
+            assert rel(xs, fix["eval_g"]) < z_tol
+            ze, _, _ = m4.latent(x)
+            rec = m4.g(ze)
+            err = float((rec - x).abs().max())
+            assert err < max(10 * fix["eval_recon_err_ref"], 1e-4), (err, fix["eval_recon_err_ref"])
+    # eval-mode forward keeps nothing for backward
+    m4.eval()
+    llx, _ = m4(x)
+    with pytest.raises(RuntimeError):
+        llx.sum().backward()
+
+
+def test_gradient_accumulation_and_zero_grad(pkg, golden_dir):
+    fix = torch.load(os.path.join(golden_dir, "tiny_32px_b4.pt"))
+    c = fix["config"]
+    st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
+    m = build(pkg, c, st0, "fp32")
+    m.train()
+    x = fix["x"].to(DEV)
+    opt = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=5e-5)
+    ll, ws = m(x)
+    (-(ll).mean() + 5e-5 * ws).backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.load_state_dict(st0)                      # same point again: grads must add up
+    ll, ws = m(x)
+    (-(ll).mean() + 5e-5 * ws).backward()
+    k = "s3_chan.1.block.1.out_block.2.conv.weight_v"
+    assert rel(dict(m.named_parameters())[k].grad, 2 * g1[k]) < 1e-3
+    opt.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    m.load_state_dict(st0)
+    ll, ws = m(x)
+    (-(ll).mean() + 5e-5 * ws).backward()
+    assert rel(dict(m.named_parameters())[k].grad, g1[k]) < 1e-3
+    opt.step()                                  # Adam consumes the flat-buffer views
+    assert not torch.equal(dict(m.named_parameters())[k].detach().cpu(), st0[k])
+
+
+def test_input_gradient(pkg, golden_dir):
+    """dLoss/dx from rnvp_flow_backward vs autograd through the oracle."""
+    c = dict(channels=3, image=16, base_dim=4, res_blocks=1, num_scales=3, B=3)
+    st0 = O.random_state(3, 16, 4, 1, 3, seed=11)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 3, 16, 16, generator=g)
+    ora = O.RealNVPOracle({k: v.clone() for k, v in st0.items()}, 3, 16, 4, 1, 3)
+    xr = x.clone().requires_grad_(True)
+    w = torch.tensor([0.3, -1.0, 2.0])
+    (ora.log_prob(xr) * w).sum().backward()
+    m = build(pkg, c, st0, "fp32")
+    m.train()
+    xd = x.to(DEV).requires_grad_(True)
+    (m.log_prob(xd) * w.to(DEV)).sum().backward()
+    assert rel(xd.grad, xr.grad) < 2e-3, rel(xd.grad, xr.grad)
+
+
+@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+def test_cfg_a_against_oracle(pkg, math, tol):
+    """BASELINE config (64x64x3, base 32, 4 blocks) at a batch the CPU oracle finishes in seconds."""
+    B = 4
+    st0 = O.random_state(3, 64, 32, 4, 5, seed=0)
+    x_img = O.synthetic_images(B, 3, 64, seed=0)
+    g = torch.Generator().manual_seed(1)
+    x, _ = O.logit_forward(x_img, torch.rand(x_img.shape, generator=g))
+    ora = O.RealNVPOracle({k: v.clone() for k, v in st0.items()}, 3, 64, 32, 4, 5)
+    with torch.no_grad():
+        z, ld, lp = ora.log_prob_parts(x)
+    c = dict(channels=3, image=64, base_dim=32, res_blocks=4, num_scales=5)
+    m = build(pkg, c, st0, math)
+    m.train()
+    zd, ldd, lld = m.latent(x.to(DEV))
+    assert rel(ldd, ld) < tol, rel(ldd, ld)
+    assert rel(lld, lp + ld) < tol, rel(lld, lp + ld)
+    # eval mode uses the running statistics the train forward just produced on both sides
+    ora.training = False
+    m.eval()
+    with torch.no_grad():
+        ll_e = ora.log_prob(x)
+        ll_d, _ = m(x.to(DEV))
+    assert rel(ll_d, ll_e) < 5 * tol, rel(ll_d, ll_e)
+
+
+def test_two_scale_config3_shape(pkg):
+    """BASELINE config 3 topology (two scales) at a reduced width, vs the oracle."""
+    c = dict(channels=3, image=32, base_dim=8, res_blocks=2, num_scales=2)
+    st0 = O.random_state(3, 32, 8, 2, 2, seed=4)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4, 3, 32, 32, generator=g)
+    ora = O.RealNVPOracle({k: v.clone() for k, v in st0.items()}, 3, 32, 8, 2, 2)
+    with torch.no_grad():
+        ll = ora.log_prob(x)
+    m = build(pkg, c, st0, "fp32")
+    m.train()
+    with torch.no_grad():
+        lld, _ = m(x.to(DEV))
+    assert rel(lld, ll) < 1e-5
+
+
+def test_full_size_properties(pkg):
+    """BASELINE config 2 size (B=256) -- size-independent properties instead of the oracle:
+    g(f(x)) round trip in the fp32 tier, per-sample independence in eval mode, determinism."""
+    B = 256
+    st0 = O.random_state(3, 64, 32, 4, 5, seed=0, scale=0.2)
+    c = dict(channels=3, image=64, base_dim=32, res_blocks=4, num_scales=5)
+    m = build(pkg, c, st0, "fp32")
+    x_img = O.synthetic_images(B, 3, 64, seed=3).to(DEV)
+    x, _ = pkg.logit_transform(x_img)
+    m.eval()
+    z, ld, ll = m.latent(x)
+    rec = m.g(z)
+    assert float((rec - x).abs().max()) < 1e-3
+    z2, ld2, ll2 = m.latent(x[:7].contiguous())
+    assert rel(ll2, ll[:7]) < 1e-5              # eval mode: no cross-sample coupling
+    z3, _, ll3 = m.latent(x)
+    assert torch.equal(z3, z)
+    m.set_math("tf32")
+    _, _, ll_t = m.latent(x)
+    assert rel(ll_t, ll) < 1e-3

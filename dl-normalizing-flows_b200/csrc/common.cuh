@@ -93,6 +93,16 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits cleared).  tcgen05 kind::tf32 simply
+// ignores the low bits (truncation, biased towards zero); tensors that exist only as conv operands are
+// therefore rounded by their producer when the TF32 tier is active.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float maybe_round(float x, int on) { return on ? round_tf32(x) : x; }
+
 // mean / rstd / scale / shift of one BN channel from (sum, sumsq) over `count` values
 struct BnCoef { float mean, rstd, scale, shift, var; };
 __device__ __forceinline__ BnCoef bn_coef_from_sums(double s, double ss, double count, float gamma, float beta) {

@@ -1,6 +1,424 @@
-// placeholder until the tcgen05 kernels land
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, TF32 operands, fp32 accumulate.
+//
+//   forward / dgrad :  y[p,n] = sum_tap sum_k x[p+tap,k] * w[tap][n][k]  (+bias) (+res)  [+ BN stats]
+//   wgrad           :  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]
+//
+// Operands stay fp32 in HBM (NHWC, channel stride padded to 32 floats = one 128-byte swizzle row)
+// and are read by the tensor core as TF32 (kind::tf32), so no conversion pass exists.
+//
+// forward: CTA tile = 128 output pixels x BN channels.  The A tile of one (tap, 32-channel chunk)
+// is ONE 4-D TMA box (32 ch, bw, bh, bn) with bw*bh*bn = 128 whose W/H coordinates are shifted by
+// the tap: out-of-image pixels are zero-filled by TMA, so the 3x3 halo costs no instructions and no
+// im2col buffer.  B is a 3-D box over w[tap][n][k].  Both land in 128B-swizzled, K-major smem and
+// feed tcgen05.mma (M=128, N=BN, K=8) x4 per chunk; the accumulator lives in TMEM.  Warp roles:
+// warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue (tcgen05.ld, bias,
+// residual, store, per-channel sum / sum-of-squares for the next batch norm via shuffles).
+//
+// wgrad: both operands are MN-major views of the same kind of TMA tiles (pixels are the GEMM K
+// dimension): A = dy tile (M = out channels), B = tap-shifted x tile (N = in channels); one CTA
+// owns a (n-tile, k-tile, tap-group, pixel-range) slab, keeps up to 512 TMEM columns of partial dw
+// and flushes them with fp32 atomics.
+#include <cuda.h>
 #include "kernels.h"
+
 namespace rnvp {
-int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) { (void)a; (void)st; set_error("tf32 conv not built"); return RNVP_ERR_INVALID; }
-int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) { (void)a; (void)st; set_error("tf32 wgrad not built"); return RNVP_ERR_INVALID; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive columns: thread i of the warp gets row (lane base + i), 32 columns
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (sm_100 version 1), 128-byte swizzle
+//   K-major : 8-row x 128B atoms stacked every SBO bytes; LBO unused
+//   MN-major: 32 MN-elements x 8 K-rows atoms; next 32 MN-elements at LBO, next 8 K-rows at SBO
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// column sums over the 32 lanes of a warp for 32 per-lane values: lane l ends with sum_lanes v[l]
+// (recursive halving: 31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      float keep = hi ? v[j + off] : v[j];
+      float send = hi ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
+
+struct ConvTcParams {
+  const float* bias;
+  const float* res;
+  float* y;
+  double* stats;
+  int P, n, ldy, taps, kchunks;      // kchunks = kpad / 32
+  int S, bw, bh, bn;                 // pixel box decomposition, bw*bh*bn = 128
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmB,
+                                                                   const ConvTcParams prm) {
+  constexpr int B_TILE_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float red_sum[4][BN];
+  __shared__ float red_sq[4][BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n0 = blockIdx.y * BN;
+  const int p0 = m_tile * 128;
+  const int total_iters = prm.taps * prm.kchunks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // pixel tile origin in (w, h, image) coordinates
+      const int hw = prm.S * prm.S;
+      const int img0 = p0 / hw;
+      const int row0 = (p0 % hw) / prm.S;          // bw == S whenever bh > 1 or bn > 1 matters
+      const int col0 = (p0 % hw) % prm.S;
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int tap = it / prm.kchunks, kc = it % prm.kchunks;
+        int dy = 0, dx = 0;
+        if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        uint8_t* a_dst = smem + s * STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_TILE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
+        tma_load_3d(b_dst, &tmB, &full_bar[s], kc * 32, n0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {           // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
+          uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
+          uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
+      }
+      umma_commit(&acc_bar);                    // accumulator complete
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int p = p0 + row;
+    const bool pvalid = p < prm.P;
+    mbar_wait(&acc_bar, 0);
+    tc_fence_after();
+    float* yrow = prm.y + (int64_t)p * prm.ldy;
+    const float* rrow = prm.res ? prm.res + (int64_t)p * prm.ldy : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+      const int nb = n0 + c0;
+      if (nb < prm.n) {
+        const bool full = nb + 32 <= prm.n;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = prm.bias ? *reinterpret_cast<const float4*>(prm.bias + nb + j) : make_float4(0, 0, 0, 0);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+          if (pvalid) {
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 r4 = *reinterpret_cast<const float4*>(rrow + nb + j);
+                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(yrow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int n = nb + j;
+            if (n < prm.n) {
+              v[j] += prm.bias ? prm.bias[n] : 0.f;
+              if (pvalid) {
+                if (rrow) v[j] += rrow[n];
+                yrow[n] = v[j];
+              }
+            } else {
+              v[j] = 0.f;
+            }
+          }
+        }
+        if (prm.stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (!pvalid) v[j] = 0.f;
+            sq[j] = v[j] * v[j];
+          }
+          float s1 = warp_transpose_sum(v, lane);
+          float s2 = warp_transpose_sum(sq, lane);
+          red_sum[q][c0 + lane] = s1;
+          red_sq[q][c0 + lane] = s2;
+        }
+      } else if (prm.stats) {
+        red_sum[q][c0 + lane] = 0.f;
+        red_sq[q][c0 + lane] = 0.f;
+      }
+    }
+    if (prm.stats) {
+      // combine the four epilogue warps (named barrier over the 128 epilogue threads)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int t = threadIdx.x - 64;
+      for (int c = t; c < BN; c += 128) {
+        int n = n0 + c;
+        if (n < prm.n) {
+          float s1 = red_sum[0][c] + red_sum[1][c] + red_sum[2][c] + red_sum[3][c];
+          float s2 = red_sq[0][c] + red_sq[1][c] + red_sq[2][c] + red_sq[3][c];
+          atomicAdd(&prm.stats[n], (double)s1);
+          atomicAdd(&prm.stats[prm.n + n], (double)s2);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    return RNVP_ERR_CUDA;
+  }
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                   box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+    return RNVP_ERR_CUDA;
+  }
+  return RNVP_OK;
+}
+
+// pixel box (bw, bh, bn) covering `npix` consecutive NHWC pixels; false if S does not allow it
+static bool pixel_box(int S, int npix, int* bw, int* bh, int* bn) {
+  if (S <= 0 || (S & (S - 1)) != 0 || S > npix) return false;     // power of two, at most npix wide
+  *bw = S;
+  *bh = (npix / S) < S ? (npix / S) : S;
+  *bn = npix / (*bw * *bh);
+  return (*bw) * (*bh) * (*bn) == npix && *bn <= 256;
+}
+
+// activation map over x [B][S][S][ld] fp32 with a (32, bw, bh, bn) box
+static int make_act_map(CUtensorMap* m, const float* x, int B, int S, int ld, int bw, int bh, int bn) {
+  cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  return encode_map(m, x, 4, dims, strides, box);
+}
+
+bool tf32_supported(int S) {
+  int a, b, c;
+  return pixel_box(S, 128, &a, &b, &c);
+}
+
+template <int BN>
+static int launch_fwd(const ConvArgs& a, const ConvTcParams& prm, const CUtensorMap& tmA, cudaStream_t st) {
+  CUtensorMap tmB;
+  cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
+  cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+  RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
+  constexpr int smem = TC_STAGES * (A_TILE_BYTES + BN * 128) + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(prm.P, 128), ceil_div(a.n, BN));
+  conv_fwd_tf32_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, prm);
+  RNVP_LAUNCH_CHECK();
+  return RNVP_OK;
+}
+
+int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
+  const int P = a.B * a.S * a.S;
+  if (P == 0) return RNVP_OK;
+  int bw, bh, bn;
+  if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0)
+    return k_conv_fwd_fp32(a, st);          // shapes the TMA box cannot express: CUDA-core kernel
+  RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "conv: taps=%d", a.taps);
+  RNVP_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0,
+               "conv operands must be 16-byte aligned");
+  CUtensorMap tmA;
+  RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
+  ConvTcParams prm{};
+  prm.bias = a.bias; prm.res = a.res; prm.y = a.y; prm.stats = a.stats;
+  prm.P = P; prm.n = a.n; prm.ldy = a.ldy; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
+  prm.S = a.S; prm.bw = bw; prm.bh = bh; prm.bn = bn;
+  if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);
+  if (a.n <= 64) return launch_fwd<64>(a, prm, tmA, st);
+  return launch_fwd<128>(a, prm, tmA, st);
+}
+
+int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
+  return k_conv_wgrad_fp32(a, st);          // replaced below once the tcgen05 wgrad kernel lands
+}
+
+}  // namespace rnvp

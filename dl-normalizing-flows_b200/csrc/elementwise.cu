@@ -221,7 +221,7 @@ int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream
 __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict__ h, int64_t n4, int C, int ld,
                                const double* __restrict__ sums, double count,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                               float* run_mean, float* run_var, float* save, int mode) {
+                               float* run_mean, float* run_var, float* save, int mode, int rnd) {
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
   float* s_shift = sm + C;
@@ -252,21 +252,22 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
     int c = (int)(e % l4) * 4;
     if (c >= C) continue;
     float4 v = x[e];
-    v.x = fmaxf(fmaf(v.x, s_scale[c + 0], s_shift[c + 0]), 0.f);
-    v.y = fmaxf(fmaf(v.y, s_scale[c + 1], s_shift[c + 1]), 0.f);
-    v.z = fmaxf(fmaf(v.z, s_scale[c + 2], s_shift[c + 2]), 0.f);
-    v.w = fmaxf(fmaf(v.w, s_scale[c + 3], s_shift[c + 3]), 0.f);
+    v.x = maybe_round(fmaxf(fmaf(v.x, s_scale[c + 0], s_shift[c + 0]), 0.f), rnd);
+    v.y = maybe_round(fmaxf(fmaf(v.y, s_scale[c + 1], s_shift[c + 1]), 0.f), rnd);
+    v.z = maybe_round(fmaxf(fmaf(v.z, s_scale[c + 2], s_shift[c + 2]), 0.f), rnd);
+    v.w = maybe_round(fmaxf(fmaf(v.w, s_scale[c + 3], s_shift[c + 3]), 0.f), rnd);
     h[e] = v;
   }
 }
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var, float* save, int mode,
-              cudaStream_t st) {
+              int tf32_round, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, "bn_relu: C=%d ld=%d unsupported", C, ld);
   int64_t n4 = (int64_t)P * ld / 4;
   bn_relu_kernel<<<grid_for(n4, kThreads * 2), kThreads, 2 * C * sizeof(float), st>>>(
-      (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta, run_mean, run_var, save, mode);
+      (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta, run_mean, run_var, save, mode,
+      tf32_round);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -444,7 +445,7 @@ int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st) {
 __global__ void cpl_in_build_kernel(const float* __restrict__ x, CplGeom g, const double* __restrict__ sums,
                                     double count, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float* run_mean, float* run_var,
-                                    float* __restrict__ save, int training, float4* __restrict__ h0) {
+                                    float* __restrict__ save, int training, float4* __restrict__ h0, int rnd) {
   __shared__ float s_scale[kMaxCio], s_shift[kMaxCio];
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
     BnCoef k = training ? bn_coef_from_sums(sums[c], sums[g.cio + c], count, gamma[c], beta[c])
@@ -475,7 +476,7 @@ __global__ void cpl_in_build_kernel(const float* __restrict__ x, CplGeom g, cons
       if (j < 2 * g.cio) {
         int c = j < g.cio ? j : j - g.cio;
         float u = fmaf(x[(int64_t)p * g.C + g.in_off + c] * m, s_scale[c], s_shift[c]);
-        v = fmaxf(j < g.cio ? u : -u, 0.f);
+        v = maybe_round(fmaxf(j < g.cio ? u : -u, 0.f), rnd);
       } else if (g.ckbd && j == 2 * g.cio) {
         v = m;                                   // relu(mask) = mask (modules_realnvp.py:275-276,259)
       }
@@ -486,11 +487,11 @@ __global__ void cpl_in_build_kernel(const float* __restrict__ x, CplGeom g, cons
 }
 int k_cpl_in_build(const float* x, CplGeom g, const double* sums, double count, const float* gamma,
                    const float* beta, float* run_mean, float* run_var, float* save, int training,
-                   float* h0, cudaStream_t st) {
+                   float* h0, int tf32_round, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   int64_t total = (int64_t)g.P() * (g.cin_pad / 4);
   cpl_in_build_kernel<<<grid_for(total, kThreads * 2), kThreads, 0, st>>>(
-      x, g, sums, count, gamma, beta, run_mean, run_var, save, training, (float4*)h0);
+      x, g, sums, count, gamma, beta, run_mean, run_var, save, training, (float4*)h0, tf32_round);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -695,7 +696,7 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
                                  double count, const float* __restrict__ dll,
                                  const float* __restrict__ scale_p, const float* __restrict__ sshift_p,
                                  float* __restrict__ dst, float* __restrict__ dxdir, float* dscale,
-                                 float* dsshift) {
+                                 float* dsshift, int rnd) {
   __shared__ float s_m1[kMaxCio], s_m2[kMaxCio];
   __shared__ float s_red[2];
   float kn = (float)(sums2[2 * g.cio] / count);
@@ -725,8 +726,8 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
       float es = expf(s);
       float xv = x[(int64_t)p * g.C + g.on_off + c];
       float ds = (dxp * xv * es + dl_b) * keep;
-      drow[c] = dxp * keep;
-      drow[g.cio + c] = ds * scale * (1.f - th * th);
+      drow[c] = maybe_round(dxp * keep, rnd);
+      drow[g.cio + c] = maybe_round(ds * scale * (1.f - th * th), rnd);
       dxdir[(int64_t)p * g.cio + c] = dxp * es;
       a_scale += ds * th;
       a_shift += ds;
@@ -747,11 +748,11 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
 }
 int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const float* stt, CplGeom g,
                 const float* save, const double* sums2, double count, const float* dll, const float* scale,
-                const float* sshift, float* dst, float* dxdir, float* dscale, float* dsshift,
+                const float* sshift, float* dst, float* dxdir, float* dscale, float* dsshift, int tf32_round,
                 cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   cpl_bwd_b_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift);
+      dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift, tf32_round);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -938,7 +939,7 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 
 // grid (pad32(max_cout), njobs); v is (cout, cin, taps) with taps innermost (NCHW-style weight).
 // Block `co` writes row co of wf and column co of wb completely, zeros included.
-__global__ void weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase) {
+__global__ void weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase, int rnd) {
   __shared__ float sm[8];
   const WnJob j = jobs[blockIdx.y];
   const int co = blockIdx.x;
@@ -958,18 +959,20 @@ __global__ void weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __r
   if (co < j.npad_f) {
     for (int e = threadIdx.x; e < j.taps * j.kpad_f; e += blockDim.x) {
       int tap = e / j.kpad_f, ci = e % j.kpad_f;
-      wf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci] = (valid && ci < j.cin) ? v[ci * j.taps + tap] * f : 0.f;
+      wf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci] =
+          (valid && ci < j.cin) ? maybe_round(v[ci * j.taps + tap] * f, rnd) : 0.f;
     }
   }
   for (int e = threadIdx.x; e < j.taps * j.npad_b; e += blockDim.x) {
     int tap = e / j.npad_b, ci = e % j.npad_b;
     wb[((int64_t)(j.taps - 1 - tap) * j.npad_b + ci) * j.kpad_b + co] =
-        (valid && ci < j.cin) ? v[ci * j.taps + tap] * f : 0.f;
+        (valid && ci < j.cin) ? maybe_round(v[ci * j.taps + tap] * f, rnd) : 0.f;
   }
 }
-int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, cudaStream_t st) {
+int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
+                     cudaStream_t st) {
   if (njobs == 0) return RNVP_OK;
-  weightnorm_fwd_kernel<<<dim3(pad_to(max_cout, 32), njobs), 128, 0, st>>>(jobs_dev, wbase);
+  weightnorm_fwd_kernel<<<dim3(pad_to(max_cout, 32), njobs), 128, 0, st>>>(jobs_dev, wbase, tf32_round);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

@@ -33,7 +33,7 @@ int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream
 //   mode 2 (recompute in backward): scale/shift read back from `save`
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var,
-              float* save, int mode, cudaStream_t st);
+              float* save, int mode, int tf32_round, cudaStream_t st);
 // gm = g * 1[h>0] written to gm_out; sums2[0:C] += sum gm, sums2[C:2C] += sum gm*xhat
 int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C, int ld,
                     const float* save, double* sums2, cudaStream_t st);
@@ -46,7 +46,7 @@ int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, i
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
 int k_cpl_in_build(const float* x, CplGeom g, const double* sums, double count, const float* gamma,
                    const float* beta, float* run_mean, float* run_var, float* save, int training,
-                   float* h0, cudaStream_t st);
+                   float* h0, int tf32_round, cudaStream_t st);
 int k_cpl_fwd_a(const float* x, const float* stt, CplGeom g, const float* scale, const float* sshift,
                 float* xprime, double* sums, double* logdet_acc, int training, cudaStream_t st);
 int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g, const double* sums,
@@ -61,7 +61,7 @@ int k_cpl_bwd_a(const float* dy, const float* xprime, CplGeom g, const float* sa
 int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const float* stt, CplGeom g,
                 const float* save, const double* sums2, double count, const float* dll,
                 const float* scale, const float* sshift, float* dst, float* dxdir,
-                float* dscale, float* dsshift, cudaStream_t st);
+                float* dscale, float* dsshift, int tf32_round, cudaStream_t st);
 int k_cpl_in_bwd_a(const float* dh0, const float* x, CplGeom g, const float* save, double* sums3,
                    cudaStream_t st);
 int k_cpl_in_bwd_b(const float* dh0, const float* x, const float* dxdir, const float* dy, CplGeom g,
@@ -93,7 +93,8 @@ struct WnJob {
   int npad_f, kpad_f, npad_b, kpad_b;
 };
 // writes every element of wf and wb (zero in the padding), so the arena needs no clearing
-int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, cudaStream_t st);
+int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
+                     cudaStream_t st);
 int k_weightnorm_bwd(const WnJob* jobs_dev, int njobs, int max_cout, const float* wbase,
                      const float* dwbase, cudaStream_t st);
 

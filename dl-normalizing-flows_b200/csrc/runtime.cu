@@ -376,13 +376,14 @@ int net_forward(const Ctx& c, int ci, int training) {
   const double count = (double)Pn * p->world;
   CplAct A = cpl_act(p, d, c.B, c.mode);
   float* H = c.scratch();
+  const int rnd = p->math == RNVP_MATH_TF32;
   auto bias = [&](const ConvDesc& cv) { return cv.has_bias ? P_<float>(p, d, ci, cv.slot_bias) : nullptr; };
   auto bn = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
     if (training) RNVP_TRY(sync_stats(c, c.sf(b.sf), 2 * b.C));
     return k_bn_relu(x, H, Pn, b.C, ld, training ? c.sf(b.sf) : nullptr, count, P_<float>(p, d, ci, b.slot_w),
                      P_<float>(p, d, ci, b.slot_b), P_<float>(p, d, ci, b.slot_rm),
-                     P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, c.st);
+                     P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, rnd, c.st);
   };
   auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
   const ConvDesc* cv = d.convs.data();
@@ -426,7 +427,8 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
   auto recompute = [&](int bi, const float* x) {
     const BnDesc& b = d.bns[bi];
-    return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2, c.st);
+    return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2,
+                     p->math == RNVP_MATH_TF32, c.st);
   };
   // BN+ReLU backward in place on g: g <- d(pre-BN input); out==nullptr: in place, else (+=) into out
   auto bn_bwd = [&](int bi, float* g, const float* x, float* out, int accumulate) -> int {
@@ -489,7 +491,8 @@ int coupling_forward(const Ctx& c, int ci, const float* x, float* y, float* logJ
   }
   RNVP_TRY(k_cpl_in_build(x, g, c.sf(d.sf_in), count, P_<float>(p, d, ci, SLOT_INBN_W),
                           P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
-                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0), c.st));
+                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0),
+                          p->math == RNVP_MATH_TF32, c.st));
   RNVP_TRY(net_forward(c, ci, training));
   RNVP_TRY(k_cpl_fwd_a(x, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT),
                        c.act(ci, A.xprime), c.sf(d.sf_out), c.logdet_acc(), training, c.st));
@@ -514,7 +517,8 @@ int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int trainin
   }
   RNVP_TRY(k_cpl_in_build(y, g, c.sf(d.sf_in), count, P_<float>(p, d, ci, SLOT_INBN_W),
                           P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
-                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0), c.st));
+                          P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0),
+                          p->math == RNVP_MATH_TF32, c.st));
   RNVP_TRY(net_forward(c, ci, training));
   RNVP_TRY(k_cpl_inv(y, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
                      P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), x, c.st));
@@ -542,7 +546,7 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
   RNVP_TRY(sync_stats(c, c.sb(d.sb_cpl), 2 * d.cio + 1));
   RNVP_TRY(k_cpl_bwd_b(dy, c.act(ci, A.xprime), x, c.act(ci, A.st), g, c.save(d.save_out), c.sb(d.sb_cpl), count,
                        dll, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), dst, dxdir,
-                       G_(p, ci, SLOT_SCALE), G_(p, ci, SLOT_SSHIFT), c.st));
+                       G_(p, ci, SLOT_SCALE), G_(p, ci, SLOT_SSHIFT), p->math == RNVP_MATH_TF32, c.st));
   RNVP_TRY(net_backward(c, ci, dst, dh0));
   RNVP_TRY(k_cpl_in_bwd_a(dh0, x, g, c.save(d.save_in), c.sb(d.sb_in), c.st));
   RNVP_TRY(sync_stats(c, c.sb(d.sb_in), 2 * d.cio));
@@ -553,7 +557,8 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
 }
 
 int materialize_weights(const Ctx& c, int first_job, int njobs) {
-  return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(), c.st);
+  return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(),
+                          c.p->math == RNVP_MATH_TF32, c.st);
 }
 
 int zero_pass(const Ctx& c, bool backward) {
@@ -1061,7 +1066,7 @@ int rnvp_weightnorm_forward(const float* v, const float* g, float* wf, float* wb
   RNVP_TRY(s.alloc(sizeof(WnJob) / 4 + 1, st));
   RNVP_CUDA(cudaMemcpyAsync(s.p, &j, sizeof(j), cudaMemcpyHostToDevice, st));
   RNVP_CUDA(cudaStreamSynchronize(st));
-  return k_weightnorm_fwd(reinterpret_cast<WnJob*>(s.p), 1, cout, wf, st);
+  return k_weightnorm_fwd(reinterpret_cast<WnJob*>(s.p), 1, cout, wf, 0, st);
 }
 int rnvp_weightnorm_backward(const float* v, const float* g, const float* dwf, float* dv, float* dg, int cout,
                              int cin, int ksize, void* stream) {

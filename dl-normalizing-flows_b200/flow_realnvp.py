@@ -87,6 +87,8 @@ class RealNVP(nn.Module):
         """'tf32' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core fp32, 1e-5 parity tier)."""
         import rnvp_cabi
         self.engine().set_math({"fp32": rnvp_cabi.MATH_FP32, "tf32": rnvp_cabi.MATH_TF32}[mode])
+        for cpl in self._couplings():
+            cpl.set_math(mode)
 
     # -- layout transforms (flow_realnvp.py:121-193) -------------------------------------- #
     def squeeze(self, x):

@@ -112,6 +112,7 @@ class AbstractCoupling(nn.Module):
         self.weight_norm = hps.weight_norm
         self.coupling_bn = hps.coupling_bn
         self._engine = None
+        self._math = None                 # None = package default; set through set_math()
 
     def build_mask(self, size, config=1.):
         """(1,1,size,size) float mask, mask[i,j] = (config+i+j) mod 2 (modules_realnvp.py:211-226)."""
@@ -134,10 +135,22 @@ class AbstractCoupling(nn.Module):
     def _shape(self):
         raise NotImplementedError
 
+    def _all_engines(self):
+        out = [self._engine] if self._engine is not None else []
+        return out + list(self.__dict__.get("_engines_by_size", {}).values())
+
+    def set_math(self, mode):
+        """'tf32' / 'fp32' arithmetic tier for this module's stand-alone calls (None = default)."""
+        import rnvp_cabi
+        self._math = None if mode is None else {"fp32": rnvp_cabi.MATH_FP32, "tf32": rnvp_cabi.MATH_TF32}[mode]
+        for e in self._all_engines():
+            e.set_math(_eng._DEFAULT_MATH if self._math is None else self._math)
+
     def _own_engine(self):
         if self._engine is None:
             c, s, d = self._shape()
-            self._engine = _eng.Engine.for_coupling(self._KIND, c, s, d, int(self.mask_config), self.res_blocks, self)
+            self._engine = _eng.Engine.for_coupling(self._KIND, c, s, d, int(self.mask_config), self.res_blocks, self,
+                                                    math=self._math)
         return self._engine
 
     def forward(self, x, reverse=False):
@@ -212,7 +225,7 @@ class ChannelwiseAffineCoupling(AbstractCoupling):
         engines = self.__dict__.setdefault("_engines_by_size", {})
         if s not in engines:
             c, _, d = self._dims
-            engines[s] = _eng.Engine.for_coupling(1, c, s, d, int(self.mask_config), self.res_blocks, self)
+            engines[s] = _eng.Engine.for_coupling(1, c, s, d, int(self.mask_config), self.res_blocks, self, math=self._math)
         eng = engines[s]
         if reverse:
             with torch.no_grad():

@@ -155,3 +155,13 @@ def test_conv_fp32(pkg, shape):
     B, S, cin, cout, k = shape
     _conv_case(pkg, B, S, cin, cout, k, 0)
     _conv_case(pkg, B, S, cin, cout, k, 0, seed=1, with_res=False)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 7, 32, 3), (3, 4, 32, 32, 1), (2, 16, 64, 6, 1), (1, 4, 97, 64, 3),
+                                   (5, 2, 12, 8, 3), (2, 64, 32, 32, 3), (4, 8, 256, 512, 1), (2, 32, 64, 64, 3),
+                                   (3, 8, 160, 96, 3), (40, 4, 512, 512, 1)])
+def test_conv_tf32(pkg, shape):
+    """tcgen05 kind::tf32 implicit GEMM (TMA-fed, TMEM accumulator) vs the fp32 torch reference."""
+    B, S, cin, cout, k = shape
+    _conv_case(pkg, B, S, cin, cout, k, 1)
+    _conv_case(pkg, B, S, cin, cout, k, 1, seed=1, with_res=False)

@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the RealNVP hot path (BASELINE.json: train imgs/s, RealNVP 64x64x3, base 32, 4 blocks).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun by the driver)
+  python bench.py --impl reference ...                   (the reference algorithm on the host cores)
+
+One "step" = one training step on a batch of synthetic dequantised images: logit transform, forward
+log-likelihood through the multi-scale coupling stack, loss, backward, Adam update.
+
+  value : device-timed throughput with the uint8 batch already resident in HBM
+  e2e   : the same step through the public API from pinned HOST buffers (uint8 H2D copy and the
+          `.item()` read of the loss inside the timed region), i.e. what train.py:176-200 does
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+warnings.filterwarnings("ignore")
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+CFG = dict(channels=3, image=64, base_dim=32, res_blocks=4, num_scales=5)
+GFLOP_FWD_PER_IMG = 11.9634          # s/t convs only, multiply-add = 2
+METRIC = "train imgs/s RealNVP 64x64x3 (fwd log-lik + bwd + Adam)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config 2: 256)")
+    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--mode", default="train", choices=["train", "sample"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prof", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2 and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower() == "active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# the reference algorithm on the CPU (oracle port)
+# ------------------------------------------------------------------------------------------
+def cpu_train_step_factory(batch):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import realnvp_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    st = O.random_state(CFG["channels"], CFG["image"], CFG["base_dim"], CFG["res_blocks"], CFG["num_scales"], seed=0)
+    for k, v in st.items():
+        if O.is_trainable(k) and v.is_floating_point():
+            v.requires_grad_(True)
+    ora = O.RealNVPOracle(st, CFG["channels"], CFG["image"], CFG["base_dim"], CFG["res_blocks"], CFG["num_scales"])
+    params = [v for k, v in st.items() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=5e-4, weight_decay=5e-5)
+    x_img = O.synthetic_images(batch, CFG["channels"], CFG["image"], seed=0)
+
+    def step():
+        opt.zero_grad()
+        noise = torch.rand(x_img.shape)
+        x, ld = O.logit_forward(x_img, noise)
+        ll, ws = ora.forward(x)
+        loss = -(ll + ld).mean() + 5e-5 * ws
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step, torch.get_num_threads()
+
+
+def cpu_sample_step_factory(batch):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import realnvp_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    st = O.random_state(CFG["channels"], CFG["image"], CFG["base_dim"], CFG["res_blocks"], CFG["num_scales"], seed=0)
+    ora = O.RealNVPOracle(st, CFG["channels"], CFG["image"], CFG["base_dim"], CFG["res_blocks"], CFG["num_scales"])
+    ora.training = False
+
+    def step():
+        with torch.no_grad():
+            z = torch.randn(batch, CFG["channels"], CFG["image"], CFG["image"])
+            return float(O.logit_inverse(ora.g(z)).mean())
+    return step, torch.get_num_threads()
+
+
+def time_cpu(step, warmup, steps, budget_s=25.0):
+    for _ in range(warmup):
+        step()
+    ts = []
+    t_all = time.time()
+    for _ in range(steps):
+        t0 = time.time()
+        step()
+        ts.append(time.time() - t0)
+        if time.time() - t_all > budget_s:
+            break
+    ts.sort()
+    return ts[len(ts) // 2], len(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 64 if args.mode == "train" else 64           # BASELINE configs[0]: batch 64 on the CPU
+    factory = cpu_train_step_factory if args.mode == "train" else cpu_sample_step_factory
+    step, threads = factory(batch)
+    warm = min(args.warmup, 1)
+    med, n = time_cpu(step, warm, max(1, min(args.steps, 5)), budget_s=120.0)
+    v = batch / med
+    unit = "img/s"
+    out = {"metric": METRIC if args.mode == "train" else "sample imgs/s RealNVP 64x64x3", "value": v, "unit": unit,
+           "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "RealNVP 64x64x3->4x4x48, 4 res-blocks, base-dim 32 (BASELINE configs[0])",
+                      "batch_per_step": batch, "note": "oracle port of the reference algorithm, torch CPU ops"},
+           "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                            "sample": f"{n} steps of batch {batch} ({args.mode})"},
+           "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------
+# the B200 path
+# ------------------------------------------------------------------------------------------
+def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
+    """Algorithmic traffic of one conv-class launch: every operand once (fp32 NHWC, padded rows)."""
+    pad = lambda v, m: (v + m - 1) // m * m
+    P = B * S * S
+    if kind in (0, 1):          # conv / dgrad: read input rows, write output rows, read weights
+        byt = 4 * (P * pad(cin, 32) + P * cout + taps * pad(cout, 16) * pad(cin, 32))
+    else:                       # wgrad: read x rows and dy rows, write dw
+        byt = 4 * (P * pad(cin, 32) + P * pad(cout, 32) + taps * pad(cout, 16) * pad(cin, 32))
+    flops = 2.0 * P * cin * cout * taps
+    return byt, flops
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("dl-normalizing-flows_b200")
+    cabi = pkg.rnvp_cabi
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cabi.check(cabi.lib.rnvp_device_ok())
+    B = args.batch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+    torch.manual_seed(0)
+    prior = torch.distributions.Normal(torch.tensor(0., device=dev), torch.tensor(1., device=dev), validate_args=False)
+    model = pkg.RealNVP(CFG["channels"], CFG["image"], prior,
+                        pkg.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True)).to(dev)
+    model.set_math(args.math)
+    if world > 1:
+        import rnvp_dp
+        model = rnvp_dp.DataParallel(model)
+    net = model.module if world > 1 else model
+    opt = torch.optim.Adam(net.parameters(), lr=5e-4, weight_decay=5e-5, fused=True)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_u8 = torch.randint(0, 256, (B, CFG["channels"], CFG["image"], CFG["image"]), generator=g,
+                            dtype=torch.uint8).pin_memory()
+    dev_u8 = host_u8.to(dev)
+
+    def train_step(x_u8):
+        opt.zero_grad(set_to_none=True)
+        x, logdet = pkg.logit_transform(x_u8)
+        ll, wscale = model(x)
+        loss = -(ll + logdet).mean() + 5e-5 * wscale
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sample_step(_):
+        with torch.no_grad():
+            imgs, _ = pkg.logit_transform(net.sample(B), reverse=True)
+        return imgs.mean()
+
+    net.train(args.mode == "train")
+    if args.mode == "sample":
+        # converged running statistics first (a sampler is used after training)
+        net.train()
+        for _ in range(3):
+            train_step(dev_u8)
+        net.eval()
+    step = train_step if args.mode == "train" else sample_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(dev_u8)
+    barrier()
+
+    # ---- device-resident timing -------------------------------------------------------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = cabi.lib.rnvp_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dev_u8)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = cabi.lib.rnvp_launch_count() - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end to end from pinned host memory ----------------------------------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step(host_u8.to(dev, non_blocking=True)) if args.mode == "train" else step(None)
+        float(out)                                            # the caller's logll.item() (train.py:196)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(te)
+    h2d = host_u8.numel() if args.mode == "train" else 0
+    d2h = 4
+
+    # ---- per-kernel-class event timing: the roofline line ---------------------------------------------
+    roof = None
+    classes = []
+    if rank == 0 and not args.no_prof:
+        cabi.lib.rnvp_prof_enable(1)
+        nprof = 2
+        for _ in range(nprof):
+            step(dev_u8)
+        rows = (C.c_double * (7 * 512))()
+        n = cabi.lib.rnvp_prof_collect(rows, 512)
+        cabi.lib.rnvp_prof_enable(0)
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                mp = json.load(f)
+            peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops": mp["bf16_tflops_sustained"], "src": "measured"}
+        except Exception:
+            pass
+        names = {0: "conv", 1: "dgrad", 2: "wgrad", 3: "bn_relu", 4: "bn_bwd"}
+        tot = 0.0
+        for i in range(max(n, 0)):
+            kind, S, taps, cin, cout, cnt, tms = [rows[7 * i + j] for j in range(7)]
+            tot += tms
+            classes.append(dict(kind=int(kind), S=int(S), taps=int(taps), cin=int(cin), cout=int(cout),
+                                launches=int(cnt), ms=tms))
+        classes.sort(key=lambda r: -r["ms"])
+        if classes:
+            top = classes[0]
+            if top["kind"] in (0, 1, 2):
+                byt, fl = conv_alg_bytes_and_flops(top["kind"], top["S"], top["taps"], top["cin"], top["cout"], B)
+                dur = top["ms"] / top["launches"] / 1e3
+                gbs, tfs = byt / dur / 1e9, fl / dur / 1e12
+                # the roof that bounds this launch: bytes/HBM vs flops/tensor (tf32 = half the bf16 rate)
+                t_hbm, t_tc = byt / (peaks["hbm_gbs"] * 1e9), fl / (peaks["bf16_tflops"] * 0.5e12)
+                if t_hbm >= t_tc:
+                    roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+                else:
+                    roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": tfs / peaks["bf16_tflops"], "traffic": None}
+                roof["kernel"] = f"{names[top['kind']]}_{args.math} S={top['S']} {int(top['taps'] ** 0.5)}x{int(top['taps'] ** 0.5)} {top['cin']}->{top['cout']}"
+                roof["launches_per_step"] = top["launches"] // nprof
+                roof["avg_us"] = dur * 1e6
+                roof["share_of_profiled_kernel_time"] = top["ms"] / tot
+                roof["peak_source"] = peaks["src"]
+                roof["algorithmic_bytes_per_launch"] = byt
+                roof["algorithmic_flops_per_launch"] = fl
+
+    # ---- CPU baseline (bounded sample of the same workload) ---------------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        factory = cpu_train_step_factory if args.mode == "train" else cpu_sample_step_factory
+        cstep, threads = factory(64)
+        med, n = time_cpu(cstep, 1, 3, budget_s=25.0)
+        cpu = {"value": 64 / med, "unit": "img/s", "cores": threads, "kind": "port",
+               "sample": f"{n} {args.mode} steps of batch 64 (BASELINE configs[0]) on the host cores"}
+
+    if rank == 0:
+        tr_flops = 3 * GFLOP_FWD_PER_IMG if args.mode == "train" else GFLOP_FWD_PER_IMG
+        out = {"metric": METRIC if args.mode == "train" else "sample imgs/s RealNVP 64x64x3",
+               "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+               "config": {"workload": "RealNVP 64x64x3, 4 res-blocks / 32 features, batch 256 per GPU "
+                                      "(BASELINE configs[1])" if args.mode == "train" else
+                                      "RealNVP 64x64x3 inverse sampling (BASELINE configs[3])",
+                          "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
+                          "parallelism": f"dp{world}" if world > 1 else "single",
+                          "l2": "per-step working set (activations ~16 GB at B=256) exceeds the 126 MB L2",
+                          "optimizer": "torch.optim.Adam(fused=True) inside the step"},
+               "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": int(launches),
+               "achieved_tflops_algorithmic": value * tr_flops / 1e3,
+               "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "kernel_classes": classes[:8]}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

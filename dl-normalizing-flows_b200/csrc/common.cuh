@@ -38,7 +38,22 @@ void set_error(const char* fmt, ...);
     }                                                \
   } while (0)
 
-#define RNVP_LAUNCH_CHECK() RNVP_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it also feeds rnvp_launch_count()
+void count_launch();
+#define RNVP_LAUNCH_CHECK()          \
+  do {                               \
+    ::rnvp::count_launch();          \
+    RNVP_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// optional per-kernel-class CUDA-event timing (rnvp_prof_*): bench.py uses it for the roofline line
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(int kind, int S, int taps, int cin, int cout, cudaStream_t st);
+  ~ProfScope();
+};
+enum { PROF_CONV = 0, PROF_DGRAD = 1, PROF_WGRAD = 2, PROF_BN = 3, PROF_BN_BWD = 4, PROF_CPL = 5 };
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -15,6 +15,10 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 constexpr int kThreads = 256;
 
 // =====================================================================================

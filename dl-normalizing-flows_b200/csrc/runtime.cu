@@ -8,9 +8,36 @@
 #include <algorithm>
 #include "kernels.h"
 
+#include <mutex>
+#include <map>
 namespace rnvp {
 const char* get_error();
+unsigned long long launch_count();
 int dp_allreduce_doubles(rnvp_plan* plan, double* buf, size_t n, cudaStream_t st);   // dp.cu
+
+// ---- per-kernel-class event timing --------------------------------------------------
+struct ProfRec { int kind, S, taps, cin, cout; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static std::mutex g_prof_mu;
+static cudaEvent_t get_event() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(int kind, int S, int taps, int cin, int cout, cudaStream_t st_) : slot(-1), st(st_) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r{kind, S, taps, cin, cout, get_event(), get_event()};
+  cudaEventRecord(r.a, st);
+  slot = (int)g_prof.size();
+  g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_prof[slot].b, st);
+}
 }
 using namespace rnvp;
 
@@ -348,6 +375,7 @@ int sync_stats(const Ctx& c, double* buf, size_t n) {
 
 int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
              const float* bias, const float* res, double* stats) {
+  ProfScope ps(dgrad ? PROF_DGRAD : PROF_CONV, S, cv.taps, dgrad ? cv.cout : cv.cin, dgrad ? cv.cin : cv.cout, c.st);
   ConvArgs a{};
   a.x = x;
   a.w = c.weights() + (dgrad ? cv.wb_off : cv.wf_off);
@@ -360,6 +388,7 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
   return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
 }
 int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy, int lddy, int S, float* dbias) {
+  ProfScope ps(PROF_WGRAD, S, cv.taps, cv.cin, cv.cout, c.st);
   WgradArgs a{};
   a.x = x; a.dy = dy; a.dw = c.dw() + cv.dw_off; a.dbias = dbias;
   a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
@@ -381,6 +410,7 @@ int net_forward(const Ctx& c, int ci, int training) {
   auto bn = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
     if (training) RNVP_TRY(sync_stats(c, c.sf(b.sf), 2 * b.C));
+    ProfScope ps(PROF_BN, S, 0, b.C, b.C, c.st);
     return k_bn_relu(x, H, Pn, b.C, ld, training ? c.sf(b.sf) : nullptr, count, P_<float>(p, d, ci, b.slot_w),
                      P_<float>(p, d, ci, b.slot_b), P_<float>(p, d, ci, b.slot_rm),
                      P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, rnd, c.st);
@@ -427,12 +457,14 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
   auto recompute = [&](int bi, const float* x) {
     const BnDesc& b = d.bns[bi];
+    ProfScope ps(PROF_BN, S, 0, b.C, b.C, c.st);
     return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2,
                      p->math == RNVP_MATH_TF32, c.st);
   };
   // BN+ReLU backward in place on g: g <- d(pre-BN input); out==nullptr: in place, else (+=) into out
   auto bn_bwd = [&](int bi, float* g, const float* x, float* out, int accumulate) -> int {
     const BnDesc& b = d.bns[bi];
+    ProfScope ps(PROF_BN_BWD, S, 0, b.C, b.C, c.st);
     RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
     RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
     return k_bn_bwd_apply(g, x, out ? out : g, accumulate, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
@@ -589,6 +621,42 @@ extern "C" {
 
 const char* rnvp_last_error(void) { return rnvp::get_error(); }
 const char* rnvp_version(void) { return "rnvp-b200 0.1 (sm_100a)"; }
+unsigned long long rnvp_launch_count(void) { return rnvp::launch_count(); }
+
+int rnvp_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(rnvp::g_prof_mu);
+  rnvp::g_prof_on = on != 0;
+  return RNVP_OK;
+}
+// Synchronises the device, aggregates the recorded intervals per kernel class and clears them.
+// Each output row is (kind, S, taps, cin, cout, launches, total_ms); returns the number of rows
+// written (<= max_rows) or a negative status.
+int rnvp_prof_collect(double* rows, int max_rows) {
+  RNVP_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lk(rnvp::g_prof_mu);
+  std::map<std::vector<int>, std::pair<long, double>> agg;
+  for (auto& r : rnvp::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[{r.kind, r.S, r.taps, r.cin, r.cout}];
+      e.first += 1;
+      e.second += ms;
+    }
+    rnvp::g_ev_pool.push_back(r.a);
+    rnvp::g_ev_pool.push_back(r.b);
+  }
+  rnvp::g_prof.clear();
+  cudaGetLastError();
+  int n = 0;
+  for (auto& kv : agg) {
+    if (n >= max_rows) break;
+    double* o = rows + 7 * n++;
+    for (int i = 0; i < 5; ++i) o[i] = kv.first[i];
+    o[5] = (double)kv.second.first;
+    o[6] = kv.second.second;
+  }
+  return n;
+}
 
 int rnvp_device_ok(void) {
   int dev = 0;

@@ -36,6 +36,9 @@ def _load():
         "rnvp_last_error": (C.c_char_p, []),
         "rnvp_version": (C.c_char_p, []),
         "rnvp_device_ok": (i32, []),
+        "rnvp_launch_count": (C.c_ulonglong, []),
+        "rnvp_prof_enable": (i32, [i32]),
+        "rnvp_prof_collect": (i32, [C.POINTER(C.c_double), i32]),
         "rnvp_plan_create": (i32, [C.POINTER(Config), C.POINTER(vp)]),
         "rnvp_plan_create_single": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(vp)]),
         "rnvp_plan_destroy": (i32, [vp]),

@@ -64,6 +64,14 @@ typedef struct rnvp_plan rnvp_plan;
 const char* rnvp_last_error(void);
 const char* rnvp_version(void);
 int rnvp_device_ok(void);                      /* 0 when cuda:current is sm_100 */
+/* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
+unsigned long long rnvp_launch_count(void);
+/* Measurement hooks: with profiling on, every conv / dgrad / wgrad / batch-norm launch is bracketed by
+ * CUDA events on its own stream.  rnvp_prof_collect synchronises, sums the intervals per kernel class
+ * into rows of 7 doubles (kind 0 conv 1 dgrad 2 wgrad 3 bn 4 bn-bwd, S, taps, cin, cout, launches,
+ * total_ms), clears the records and returns the row count.                                        */
+int rnvp_prof_enable(int on);
+int rnvp_prof_collect(double* rows_host, int max_rows);
 
 /* ---- plan ------------------------------------------------------------- */
 int rnvp_plan_create(const rnvp_config* cfg, rnvp_plan** out);

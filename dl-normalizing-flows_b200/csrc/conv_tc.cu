@@ -103,15 +103,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
 // shared-memory matrix descriptor (sm_100 version 1), 128-byte swizzle
 //   K-major : 8-row x 128B atoms stacked every SBO bytes; LBO unused
 //   MN-major: 32 MN-elements x 8 K-rows atoms; next 32 MN-elements at LBO, next 8 K-rows at SBO
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major 32-bit operands must use the "128B swizzle, 32B atom" layout (type 1): atoms of
+//             32 MN-elements x 4 K-rows (rows 128 B apart), next 4 K-rows at SBO, next 32 MN at LBO
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2 /* SWIZZLE_128B */) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
+constexpr uint32_t kLayoutSw128Base32 = 1;   // UMMA::LayoutType::SWIZZLE_128B_BASE32B
 // instruction descriptor for kind::tf32, fp32 accumulate
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -338,7 +342,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
@@ -346,7 +350,7 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
   }
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                   box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
@@ -366,11 +370,12 @@ static bool pixel_box(int S, int npix, int* bw, int* bh, int* bn) {
 }
 
 // activation map over x [B][S][S][ld] fp32 with a (32, bw, bh, bn) box
-static int make_act_map(CUtensorMap* m, const float* x, int B, int S, int ld, int bw, int bh, int bn) {
+static int make_act_map(CUtensorMap* m, const float* x, int B, int S, int ld, int bw, int bh, int bn,
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  return encode_map(m, x, 4, dims, strides, box);
+  return encode_map(m, x, 4, dims, strides, box, swz);
 }
 
 bool tf32_supported(int S) {
@@ -417,8 +422,217 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   return launch_fwd<128>(a, prm, tmA, st);
 }
 
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel:  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]   (+ dbias[n] += sum_p dy[p,n])
+//
+// GEMM view: D[M = n][N = k] += A[M][K = pixels] * B[N][K = pixels]^T with BOTH operands MN-major:
+// the TMA tiles are (32 channels x 64 pixels) boxes whose 128-byte rows are pixels, i.e. the GEMM K
+// dimension is the strided one.  One CTA owns (n-tile of <=128, k-tile of <=128, a group of taps, a
+// pixel range): per 64-pixel tile it loads the dy boxes once (A ring) and one tap-shifted x tile per
+// tap (B ring), issues 8 x (K = 8 pixels) MMAs per tap into that tap's TMEM columns, and finally
+// flushes the <=512 accumulator columns with fp32 atomics.  The bias gradient rides along as one
+// extra N=16 MMA against a constant all-ones tile.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
+constexpr int WG_A_STAGES = 2, WG_B_STAGES = 4;
+constexpr int WG_A_STAGE_BYTES = 4 * WG_BOX_BYTES;
+constexpr int WG_B_STAGE_BYTES = 4 * WG_BOX_BYTES;
+constexpr int WG_SMEM = WG_A_STAGES * WG_A_STAGE_BYTES + WG_B_STAGES * WG_B_STAGE_BYTES + WG_BOX_BYTES + 1024;
+
+struct WgradTcParams {
+  float* dw;
+  float* dbias;
+  int P, n, npad, kpad, taps;
+  int S;
+  int n_tiles, k_tiles, tap_groups, tg;     // tg = taps per group
+  int tiles_per_split, num_tiles;           // 64-pixel tiles
+  int tmem_cols;
+};
+
+__device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDy,
+                                                                     const __grid_constant__ CUtensorMap tmX,
+                                                                     const WgradTcParams prm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + WG_A_STAGES * WG_A_STAGE_BYTES;
+  float* ones = reinterpret_cast<float*>(b_ring + WG_B_STAGES * WG_B_STAGE_BYTES);
+  __shared__ __align__(8) uint64_t a_full[WG_A_STAGES], a_empty[WG_A_STAGES];
+  __shared__ __align__(8) uint64_t b_full[WG_B_STAGES], b_empty[WG_B_STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bx = blockIdx.x;
+  const int kt = bx % prm.k_tiles; bx /= prm.k_tiles;
+  const int nt = bx % prm.n_tiles; bx /= prm.n_tiles;
+  const int tgi = bx;
+  const int n0 = nt * 128, k0 = kt * 128;
+  const int tap0 = tgi * prm.tg;
+  const int ntap = min(prm.tg, prm.taps - tap0);
+  const int nA = min(4, ceil_div(min(prm.npad, pad_to(prm.n, 32)) - n0, 32));   // dy boxes (32 channels each)
+  const int nB = min(4, (prm.kpad - k0) / 32);                                 // x boxes
+  const int N = nB * 32;
+  const int t_begin = blockIdx.y * prm.tiles_per_split;
+  const int t_end = min(prm.num_tiles, t_begin + prm.tiles_per_split);
+  const bool do_bias = prm.dbias != nullptr && kt == 0 && tgi == 0;
+  const uint32_t bias_col = (uint32_t)(ntap * N);
+
+  for (int i = threadIdx.x; i < WG_BOX_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
+  fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmDy);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < WG_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_dyn(&tmem_base_slot, (uint32_t)prm.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (t_begin < t_end) {
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        const int hw = prm.S * prm.S;
+        int bi = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          const int p0 = t * 64;
+          const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
+          const int ai = t - t_begin, as = ai % WG_A_STAGES;
+          mbar_wait(&a_empty[as], ((ai / WG_A_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&a_full[as], nA * WG_BOX_BYTES);
+          for (int g = 0; g < nA; ++g)
+            tma_load_4d(a_ring + as * WG_A_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &a_full[as], n0 + 32 * g, col0, row0, img0);
+          for (int tl = 0; tl < ntap; ++tl, ++bi) {
+            const int tap = tap0 + tl;
+            int dy = 0, dx = 0;
+            if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+            const int bs = bi % WG_B_STAGES;
+            mbar_wait(&b_empty[bs], ((bi / WG_B_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&b_full[bs], nB * WG_BOX_BYTES);
+            for (int g = 0; g < nB; ++g)
+              tma_load_4d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmX, &b_full[bs], k0 + 32 * g, col0 + dx,
+                          row0 + dy, img0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_tf32(128, N, 1, 1);
+        const uint32_t idesc_bias = make_idesc_tf32(128, 16, 1, 1);
+        const uint32_t a_lbo = nA > 1 ? WG_BOX_BYTES : 0;      // nA == 1: all four M groups alias box 0
+        const uint32_t ones_addr = smem_u32(ones);
+        int bi = 0;
+        for (int t = t_begin; t < t_end; ++t) {
+          const int ai = t - t_begin, as = ai % WG_A_STAGES;
+          mbar_wait(&a_full[as], (ai / WG_A_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(a_ring + as * WG_A_STAGE_BYTES);
+          const uint32_t acc = (t != t_begin);
+          if (do_bias) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_tf32(tmem_base + bias_col, make_desc(a_addr + ks * 1024, a_lbo, 512, kLayoutSw128Base32),
+                        make_desc(ones_addr + ks * 1024, 0, 512, kLayoutSw128Base32), idesc_bias, acc | (ks != 0));
+          }
+          for (int tl = 0; tl < ntap; ++tl, ++bi) {
+            const int bs = bi % WG_B_STAGES;
+            mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(b_ring + bs * WG_B_STAGE_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)       // 8 x (K = 8 pixels = two 512-byte swizzle atoms)
+              umma_tf32(tmem_base + (uint32_t)(tl * N), make_desc(a_addr + ks * 1024, a_lbo, 512, kLayoutSw128Base32),
+                        make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
+            umma_commit(&b_empty[bs]);
+          }
+          umma_commit(&a_empty[as]);
+        }
+        umma_commit(&acc_bar);
+      }
+    } else {
+      // ===================== epilogue: TMEM -> fp32 atomics =====================
+      const int q = warp & 3;
+      const int m = q * 32 + lane;
+      const int n = n0 + m;
+      mbar_wait(&acc_bar, 0);
+      tc_fence_after();
+      const bool nvalid = n < prm.n;
+      for (int tl = 0; tl < ntap; ++tl) {
+        float* drow = prm.dw + ((int64_t)(tap0 + tl) * prm.npad + n) * prm.kpad + k0;
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * N + c0), v);
+          if (nvalid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
+          }
+        }
+      }
+      if (do_bias) {
+        float v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + bias_col, v);
+        if (nvalid) atomicAdd(prm.dbias + n, v[0]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)prm.tmem_cols);
+}
+
 int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
-  return k_conv_wgrad_fp32(a, st);          // replaced below once the tcgen05 wgrad kernel lands
+  const int P = a.B * a.S * a.S;
+  if (P == 0) return RNVP_OK;
+  int bw, bh, bn;
+  if (!pixel_box(a.S, 64, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.lddy % 32 != 0)
+    return k_conv_wgrad_fp32(a, st);
+  RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "wgrad: taps=%d", a.taps);
+  CUtensorMap tmDy, tmX;
+  // MN-major fp32 operands: 128B swizzle with 32-byte atoms (the only layout tcgen05 accepts for them)
+  RNVP_TRY(make_act_map(&tmDy, a.dy, a.B, a.S, a.lddy, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RNVP_TRY(make_act_map(&tmX, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  WgradTcParams prm{};
+  prm.dw = a.dw; prm.dbias = a.dbias;
+  prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = a.kpad; prm.taps = a.taps; prm.S = a.S;
+  prm.n_tiles = ceil_div(a.n, 128);
+  prm.k_tiles = ceil_div(a.kpad, 128);
+  const int N = a.kpad < 128 ? a.kpad : 128;
+  int tg = (512 - 32) / N;                        // taps whose accumulators fit in TMEM beside the bias columns
+  if (tg > a.taps) tg = a.taps;
+  prm.tap_groups = ceil_div(a.taps, tg);
+  prm.tg = ceil_div(a.taps, prm.tap_groups);      // balance the groups (9 taps: 9 | 5+4 | 3+3+3)
+  int cols = prm.tg * N + 32, alloc = 32;
+  while (alloc < cols) alloc <<= 1;
+  prm.tmem_cols = alloc;
+  prm.num_tiles = ceil_div(P, 64);
+  const int base = prm.n_tiles * prm.k_tiles * prm.tap_groups;
+  int splits = ceil_div(kNumSMs, base);
+  if (splits > prm.num_tiles) splits = prm.num_tiles;
+  prm.tiles_per_split = ceil_div(prm.num_tiles, splits);
+  splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
+  static bool attr_set = false;
+  if (!attr_set) {
+    RNVP_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    attr_set = true;
+  }
+  conv_wgrad_tf32_kernel<<<dim3(base, splits), TC_THREADS, WG_SMEM, st>>>(tmDy, tmX, prm);
+  RNVP_LAUNCH_CHECK();
+  return RNVP_OK;
 }
 
 }  // namespace rnvp

@@ -138,7 +138,7 @@ def _conv_case(pkg, B, S, cin, cout, k, math, seed=0, with_res=True):
     check(lib.rnvp_conv_wgrad(ptr(xn), ptr(dyn), ptr(dwf), ptr(db), B, S, kpad, cout, npad, k, kpad_b, math, _stream()))
     got_dw = dwf[:, :cout, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1).cpu()
     assert rel(got_dw, dw_ref) < (2e-5 if math == 0 else 3e-3), rel(got_dw, dw_ref)
-    assert rel(db, dy.sum((0, 2, 3))) < 2e-5
+    assert rel(db, dy.sum((0, 2, 3))) < (2e-5 if math == 0 else 2e-3)   # tf32: rides on an MMA
     vr, gr = v.clone().requires_grad_(True), gg.clone().requires_grad_(True)
     wr = vr * (gr / torch.linalg.vector_norm(vr, dim=(1, 2, 3), keepdim=True))
     (wr * dw_ref).sum().backward()

@@ -286,6 +286,7 @@ def run_b200(args):
     # ---- per-kernel-class event timing: the roofline line ---------------------------------------------
     roof = None
     classes = []
+    by_kind = {}
     if rank == 0 and not args.no_prof:
         cabi.lib.rnvp_prof_enable(1)
         nprof = 2
@@ -309,6 +310,8 @@ def run_b200(args):
             classes.append(dict(kind=int(kind), S=int(S), taps=int(taps), cin=int(cin), cout=int(cout),
                                 launches=int(cnt), ms=tms))
         classes.sort(key=lambda r: -r["ms"])
+        for r in classes:
+            by_kind[names[r["kind"]]] = by_kind.get(names[r["kind"]], 0.0) + r["ms"] / nprof
         if classes:
             top = classes[0]
             if top["kind"] in (0, 1, 2):
@@ -357,7 +360,7 @@ def run_b200(args):
                "gpu_launches": int(launches),
                "achieved_tflops_algorithmic": value * tr_flops / 1e3,
                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-               "kernel_classes": classes[:8]}
+               "kernel_time_ms_by_kind_per_step": by_kind, "kernel_classes": classes[:16]}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

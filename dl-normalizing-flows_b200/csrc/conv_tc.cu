@@ -139,7 +139,12 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward / dgrad kernel
+// forward / dgrad kernel (persistent)
+//
+// grid = min(#tiles, resident CTAs); every CTA walks tiles t = blockIdx.x, += gridDim.x.  The TMA
+// producer runs ahead across tile boundaries through a 4-stage smem ring; the accumulator is double
+// buffered in TMEM so the epilogue of tile i (TMEM -> registers -> bias/residual -> HBM, BN partial
+// sums) overlaps the loads and MMAs of tile i+1.
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
@@ -151,7 +156,8 @@ struct ConvTcParams {
   float* y;
   double* stats;
   int P, n, ldy, taps, kchunks;      // kchunks = kpad / 32
-  int S, bw, bh, bn;                 // pixel box decomposition, bw*bh*bn = 128
+  int S;
+  int m_tiles, n_tiles;
 };
 
 template <int BN>
@@ -160,21 +166,20 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
                                                                    const ConvTcParams prm) {
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment for the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full[2];
+  __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_sum[4][BN];
   __shared__ float red_sq[4][BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n0 = blockIdx.y * BN;
-  const int p0 = m_tile * 128;
-  const int total_iters = prm.taps * prm.kchunks;
+  const int iters = prm.taps * prm.kchunks;
+  const int num_tiles = prm.m_tiles * prm.n_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -183,7 +188,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);        // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
@@ -195,77 +203,99 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      // pixel tile origin in (w, h, image) coordinates
       const int hw = prm.S * prm.S;
-      const int img0 = p0 / hw;
-      const int row0 = (p0 % hw) / prm.S;          // bw == S whenever bh > 1 or bn > 1 matters
-      const int col0 = (p0 % hw) % prm.S;
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = it / prm.kchunks, kc = it % prm.kchunks;
-        int dy = 0, dx = 0;
-        if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-        uint8_t* a_dst = smem + s * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_TILE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
-        tma_load_3d(b_dst, &tmB, &full_bar[s], kc * 32, n0, tap);
+      int it_glob = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
+        const int p0 = m_tile * 128;
+        const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
+        for (int it = 0; it < iters; ++it, ++it_glob) {
+          const int s = it_glob % TC_STAGES;
+          mbar_wait(&empty_bar[s], ((it_glob / TC_STAGES) & 1) ^ 1);
+          const int tap = it / prm.kchunks, kc = it % prm.kchunks;
+          int dy = 0, dx = 0;
+          if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+          uint8_t* a_dst = smem + s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
+          tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % TC_STAGES;
-        const uint32_t ph = (it / TC_STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it_glob = 0, ti = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+        const int as = ti & 1;
+        mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int it = 0; it < iters; ++it, ++it_glob) {
+          const int s = it_glob % TC_STAGES;
+          mbar_wait(&full_bar[s], (it_glob / TC_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {           // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
-          uint64_t ad = make_desc(a_addr + k * 32, 16, 1024);
-          uint64_t bd = make_desc(b_addr + k * 32, 16, 1024);
-          umma_tf32(tmem_base, ad, bd, idesc, (it | k) != 0);
+          for (int k = 0; k < 4; ++k)             // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
+            umma_tf32(d_tmem, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                      (it | k) != 0);
+          umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
+        umma_commit(&acc_full[as]);               // accumulator of this tile complete
       }
-      umma_commit(&acc_bar);                    // accumulator complete
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
-    const int p = p0 + row;
-    const bool pvalid = p < prm.P;
-    mbar_wait(&acc_bar, 0);
-    tc_fence_after();
-    float* yrow = prm.y + (int64_t)p * prm.ldy;
-    const float* rrow = prm.res ? prm.res + (int64_t)p * prm.ldy : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-      const int nb = n0 + c0;
-      if (nb < prm.n) {
+    float acc_s[BN / 32], acc_q[BN / 32];         // per-lane column sums (column c0 + lane), n_tiles == 1
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) acc_s[i] = acc_q[i] = 0.f;
+    const bool keep_stats = prm.stats != nullptr;
+    int ti = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      const int as = ti & 1;
+      const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
+      const int p = m_tile * 128 + row;
+      const bool pvalid = p < prm.P;
+      float* yrow = prm.y + (int64_t)p * prm.ldy;
+      const float* rrow = prm.res ? prm.res + (int64_t)p * prm.ldy : nullptr;
+      mbar_wait(&acc_full[as], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ++ci) {
+        const int c0 = ci * 32;
+        const int nb = n0 + c0;
+        if (nb >= prm.n) break;
+        float v[32];
+        // residual first: its global-load latency overlaps the TMEM read
+        float r[32];
         const bool full = nb + 32 <= prm.n;
-        if (full) {
+        if (rrow != nullptr && pvalid && full) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 b4 = prm.bias ? *reinterpret_cast<const float4*>(prm.bias + nb + j) : make_float4(0, 0, 0, 0);
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            float4 r4 = *reinterpret_cast<const float4*>(rrow + nb + j);
+            r[j] = r4.x; r[j + 1] = r4.y; r[j + 2] = r4.z; r[j + 3] = r4.w;
           }
-          if (pvalid) {
-            if (rrow) {
+        } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 r4 = *reinterpret_cast<const float4*>(rrow + nb + j);
-                v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-              }
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
+        }
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        if (full) {
+          if (prm.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = *reinterpret_cast<const float4*>(prm.bias + nb + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += r[j];
+          if (pvalid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(yrow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -285,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
             }
           }
         }
-        if (prm.stats) {
+        if (keep_stats) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -294,25 +324,34 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
           }
           float s1 = warp_transpose_sum(v, lane);
           float s2 = warp_transpose_sum(sq, lane);
-          red_sum[q][c0 + lane] = s1;
-          red_sq[q][c0 + lane] = s2;
+          if (prm.n_tiles == 1) {
+            acc_s[ci] += s1;
+            acc_q[ci] += s2;
+          } else if (nb + lane < prm.n) {
+            atomicAdd(&prm.stats[nb + lane], (double)s1);
+            atomicAdd(&prm.stats[prm.n + nb + lane], (double)s2);
+          }
         }
-      } else if (prm.stats) {
-        red_sum[q][c0 + lane] = 0.f;
-        red_sq[q][c0 + lane] = 0.f;
       }
+      // this warp is done with the accumulator: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
     }
-    if (prm.stats) {
-      // combine the four epilogue warps (named barrier over the 128 epilogue threads)
+    if (keep_stats && prm.n_tiles == 1) {
+#pragma unroll
+      for (int ci = 0; ci < BN / 32; ++ci) {
+        red_sum[q][ci * 32 + lane] = acc_s[ci];
+        red_sq[q][ci * 32 + lane] = acc_q[ci];
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int t = threadIdx.x - 64;
-      for (int c = t; c < BN; c += 128) {
-        int n = n0 + c;
-        if (n < prm.n) {
+      const int tt = threadIdx.x - 64;
+      for (int c = tt; c < BN; c += 128) {
+        if (c < prm.n) {
           float s1 = red_sum[0][c] + red_sum[1][c] + red_sum[2][c] + red_sum[3][c];
           float s2 = red_sq[0][c] + red_sq[1][c] + red_sq[2][c] + red_sq[3][c];
-          atomicAdd(&prm.stats[n], (double)s1);
-          atomicAdd(&prm.stats[prm.n + n], (double)s2);
+          atomicAdd(&prm.stats[c], (double)s1);
+          atomicAdd(&prm.stats[prm.n + c], (double)s2);
         }
       }
     }
@@ -384,19 +423,26 @@ bool tf32_supported(int S) {
 }
 
 template <int BN>
-static int launch_fwd(const ConvArgs& a, const ConvTcParams& prm, const CUtensorMap& tmA, cudaStream_t st) {
+static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tmA, cudaStream_t st) {
   CUtensorMap tmB;
   cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
   cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
   constexpr int smem = TC_STAGES * (A_TILE_BYTES + BN * 128) + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    int occ = 1;
+    RNVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_tf32_kernel<BN>, TC_THREADS, smem));
+    int tmem_limit = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+    ctas_per_sm = occ < 1 ? 1 : (occ > tmem_limit ? tmem_limit : occ);
   }
-  dim3 grid(ceil_div(prm.P, 128), ceil_div(a.n, BN));
+  prm.m_tiles = ceil_div(prm.P, 128);
+  prm.n_tiles = ceil_div(a.n, BN);
+  int tiles = prm.m_tiles * prm.n_tiles;
+  int grid = kNumSMs * ctas_per_sm;
+  if (grid > tiles) grid = tiles;
   conv_fwd_tf32_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, prm);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
@@ -416,7 +462,7 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   ConvTcParams prm{};
   prm.bias = a.bias; prm.res = a.res; prm.y = a.y; prm.stats = a.stats;
   prm.P = P; prm.n = a.n; prm.ldy = a.ldy; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
-  prm.S = a.S; prm.bw = bw; prm.bh = bh; prm.bn = bn;
+  prm.S = a.S;
   if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);
   if (a.n <= 64) return launch_fwd<64>(a, prm, tmA, st);
   return launch_fwd<128>(a, prm, tmA, st);
@@ -425,26 +471,30 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // wgrad kernel:  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]   (+ dbias[n] += sum_p dy[p,n])
 //
-// GEMM view: D[M = n][N = k] += A[M][K = pixels] * B[N][K = pixels]^T with BOTH operands MN-major:
-// the TMA tiles are (32 channels x 64 pixels) boxes whose 128-byte rows are pixels, i.e. the GEMM K
-// dimension is the strided one.  One CTA owns (n-tile of <=128, k-tile of <=128, a group of taps, a
-// pixel range): per 64-pixel tile it loads the dy boxes once (A ring) and one tap-shifted x tile per
-// tap (B ring), issues 8 x (K = 8 pixels) MMAs per tap into that tap's TMEM columns, and finally
-// flushes the <=512 accumulator columns with fp32 atomics.  The bias gradient rides along as one
-// extra N=16 MMA against a constant all-ones tile.
+// GEMM view per 64-pixel tile:  D[(tap,k)][n] += X_tap[(tap,k)][pixels] * DY[n][pixels]^T with BOTH
+// operands MN-major: the TMA tiles are (32 channels x 64 pixels) boxes whose 128-byte rows are pixels,
+// i.e. the GEMM K dimension is the strided one (layout "128B swizzle, 32B atom", mandatory for MN-major
+// 32-bit operands).  The M dimension packs (tap, input channel): with <=32 input channels four
+// tap-shifted x tiles fill one M=128 operand, so narrow layers do not waste tensor-core rows.
+// One CTA owns (k-tile, n-tile, tap range, pixel range): per pixel tile it loads the dy boxes once,
+// then one 4-box A stage per M-group, issues 8 x (K = 8 pixels) MMAs per group into that group's
+// TMEM columns, and finally flushes the accumulators with coalesced fp32 atomics.  The bias gradient
+// is one more M-group whose A operand is a constant all-ones tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
-constexpr int WG_A_STAGES = 2, WG_B_STAGES = 4;
+constexpr int WG_A_STAGES = 4, WG_B_STAGES = 2;
 constexpr int WG_A_STAGE_BYTES = 4 * WG_BOX_BYTES;
 constexpr int WG_B_STAGE_BYTES = 4 * WG_BOX_BYTES;
 constexpr int WG_SMEM = WG_A_STAGES * WG_A_STAGE_BYTES + WG_B_STAGES * WG_B_STAGE_BYTES + WG_BOX_BYTES + 1024;
+constexpr int WG_MAX_GROUPS = 16;
 
 struct WgradTcParams {
   float* dw;
   float* dbias;
-  int P, n, npad, kpad, taps;
-  int S;
-  int n_tiles, k_tiles, tap_groups, tg;     // tg = taps per group
+  int P, n, npad, kpad, taps, S;
+  int n_tiles, k_tiles, tap_ranges, taps_per_range;
+  int kb;                                   // x boxes (32 channels) per tap inside a k-tile (full tiles)
+  int tpm;                                  // taps packed into one M = 128 operand
   int tiles_per_split, num_tiles;           // 64-pixel tiles
   int tmem_cols;
 };
@@ -474,17 +524,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   int bx = blockIdx.x;
   const int kt = bx % prm.k_tiles; bx /= prm.k_tiles;
   const int nt = bx % prm.n_tiles; bx /= prm.n_tiles;
-  const int tgi = bx;
+  const int tr = bx;
   const int n0 = nt * 128, k0 = kt * 128;
-  const int tap0 = tgi * prm.tg;
-  const int ntap = min(prm.tg, prm.taps - tap0);
-  const int nA = min(4, ceil_div(min(prm.npad, pad_to(prm.n, 32)) - n0, 32));   // dy boxes (32 channels each)
-  const int nB = min(4, (prm.kpad - k0) / 32);                                 // x boxes
-  const int N = nB * 32;
+  const int tap0 = tr * prm.taps_per_range;
+  const int ntap = min(prm.taps_per_range, prm.taps - tap0);
+  const int kb = min(prm.kb, (prm.kpad - k0) / 32);                     // x boxes per tap in this k-tile
+  const int nbx = min(4, ceil_div(pad_to(prm.n, 32) - n0, 32));          // dy boxes (32 channels each)
+  const int N = nbx * 32;
+  const int groups = ceil_div(ntap, prm.tpm);
   const int t_begin = blockIdx.y * prm.tiles_per_split;
   const int t_end = min(prm.num_tiles, t_begin + prm.tiles_per_split);
-  const bool do_bias = prm.dbias != nullptr && kt == 0 && tgi == 0;
-  const uint32_t bias_col = (uint32_t)(ntap * N);
+  const bool do_bias = prm.dbias != nullptr && kt == 0 && tr == 0;
+  const uint32_t bias_col = (uint32_t)(groups * N);
 
   for (int i = threadIdx.x; i < WG_BOX_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
   fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
@@ -507,25 +558,28 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       // ===================== TMA producer =====================
       if (lane == 0) {
         const int hw = prm.S * prm.S;
-        int bi = 0;
+        int ai = 0;
         for (int t = t_begin; t < t_end; ++t) {
           const int p0 = t * 64;
           const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
-          const int ai = t - t_begin, as = ai % WG_A_STAGES;
-          mbar_wait(&a_empty[as], ((ai / WG_A_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&a_full[as], nA * WG_BOX_BYTES);
-          for (int g = 0; g < nA; ++g)
-            tma_load_4d(a_ring + as * WG_A_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &a_full[as], n0 + 32 * g, col0, row0, img0);
-          for (int tl = 0; tl < ntap; ++tl, ++bi) {
-            const int tap = tap0 + tl;
-            int dy = 0, dx = 0;
-            if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-            const int bs = bi % WG_B_STAGES;
-            mbar_wait(&b_empty[bs], ((bi / WG_B_STAGES) & 1) ^ 1);
-            mbar_expect_tx(&b_full[bs], nB * WG_BOX_BYTES);
-            for (int g = 0; g < nB; ++g)
-              tma_load_4d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmX, &b_full[bs], k0 + 32 * g, col0 + dx,
-                          row0 + dy, img0);
+          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
+          mbar_wait(&b_empty[bs], ((bi / WG_B_STAGES) & 1) ^ 1);
+          mbar_expect_tx(&b_full[bs], nbx * WG_BOX_BYTES);
+          for (int g = 0; g < nbx; ++g)
+            tma_load_4d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &b_full[bs], n0 + 32 * g, col0, row0, img0);
+          for (int mg = 0; mg < groups; ++mg, ++ai) {
+            const int as = ai % WG_A_STAGES;
+            const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);       // taps in this M-group
+            mbar_wait(&a_empty[as], ((ai / WG_A_STAGES) & 1) ^ 1);
+            mbar_expect_tx(&a_full[as], tl_n * kb * WG_BOX_BYTES);
+            for (int tl = 0; tl < tl_n; ++tl) {
+              const int tap = tap0 + mg * prm.tpm + tl;
+              int dy = 0, dx = 0;
+              if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+              for (int j = 0; j < kb; ++j)
+                tma_load_4d(a_ring + as * WG_A_STAGE_BYTES + (tl * kb + j) * WG_BOX_BYTES, &tmX, &a_full[as],
+                            k0 + 32 * j, col0 + dx, row0 + dy, img0);
+            }
           }
         }
       }
@@ -533,60 +587,67 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       // ===================== MMA issuer =====================
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, N, 1, 1);
-        const uint32_t idesc_bias = make_idesc_tf32(128, 16, 1, 1);
-        const uint32_t a_lbo = nA > 1 ? WG_BOX_BYTES : 0;      // nA == 1: all four M groups alias box 0
         const uint32_t ones_addr = smem_u32(ones);
-        int bi = 0;
+        int ai = 0;
         for (int t = t_begin; t < t_end; ++t) {
-          const int ai = t - t_begin, as = ai % WG_A_STAGES;
-          mbar_wait(&a_full[as], (ai / WG_A_STAGES) & 1);
+          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
+          mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(a_ring + as * WG_A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(b_ring + bs * WG_B_STAGE_BYTES);
           const uint32_t acc = (t != t_begin);
           if (do_bias) {
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_tf32(tmem_base + bias_col, make_desc(a_addr + ks * 1024, a_lbo, 512, kLayoutSw128Base32),
-                        make_desc(ones_addr + ks * 1024, 0, 512, kLayoutSw128Base32), idesc_bias, acc | (ks != 0));
+            for (int ks = 0; ks < 8; ++ks)       // A = ones (LBO 0: all four 32-row groups alias one box)
+              umma_tf32(tmem_base + bias_col, make_desc(ones_addr + ks * 1024, 0, 512, kLayoutSw128Base32),
+                        make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
           }
-          for (int tl = 0; tl < ntap; ++tl, ++bi) {
-            const int bs = bi % WG_B_STAGES;
-            mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+          for (int mg = 0; mg < groups; ++mg, ++ai) {
+            const int as = ai % WG_A_STAGES;
+            mbar_wait(&a_full[as], (ai / WG_A_STAGES) & 1);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(b_ring + bs * WG_B_STAGE_BYTES);
+            const uint32_t a_addr = smem_u32(a_ring + as * WG_A_STAGE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)       // 8 x (K = 8 pixels = two 512-byte swizzle atoms)
-              umma_tf32(tmem_base + (uint32_t)(tl * N), make_desc(a_addr + ks * 1024, a_lbo, 512, kLayoutSw128Base32),
+              umma_tf32(tmem_base + (uint32_t)(mg * N), make_desc(a_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32),
                         make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
-            umma_commit(&b_empty[bs]);
+            umma_commit(&a_empty[as]);
           }
-          umma_commit(&a_empty[as]);
+          umma_commit(&b_empty[bs]);
         }
         umma_commit(&acc_bar);
       }
     } else {
-      // ===================== epilogue: TMEM -> fp32 atomics =====================
+      // ===================== epilogue: TMEM -> coalesced fp32 atomics =====================
       const int q = warp & 3;
-      const int m = q * 32 + lane;
-      const int n = n0 + m;
+      const int m = q * 32 + lane;               // accumulator row = (tap_local, k)
+      const int kc = kb * 32;
+      const int tl = m / kc, k = m % kc;
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
-      const bool nvalid = n < prm.n;
-      for (int tl = 0; tl < ntap; ++tl) {
-        float* drow = prm.dw + ((int64_t)(tap0 + tl) * prm.npad + n) * prm.kpad + k0;
+      for (int mg = 0; mg < groups; ++mg) {
+        const int tap_l = mg * prm.tpm + tl;
+        const bool rvalid = tl < prm.tpm && tap_l < ntap;
+        float* dst = prm.dw + ((int64_t)(tap0 + tap_l) * prm.npad + n0) * prm.kpad + k0 + k;
         for (int c0 = 0; c0 < N; c0 += 32) {
           float v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * N + c0), v);
-          if (nvalid) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mg * N + c0), v);
+          if (rvalid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(drow + c0 + j, v[j]);
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < prm.n) atomicAdd(dst + (int64_t)(c0 + j) * prm.kpad, v[j]);
           }
         }
       }
       if (do_bias) {
-        float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + bias_col, v);
-        if (nvalid) atomicAdd(prm.dbias + n, v[0]);
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          float v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + bias_col + c0, v);
+          if (m == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < prm.n) atomicAdd(prm.dbias + n0 + c0 + j, v[j]);
+          }
+        }
       }
     }
   }
@@ -611,16 +672,22 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = a.kpad; prm.taps = a.taps; prm.S = a.S;
   prm.n_tiles = ceil_div(a.n, 128);
   prm.k_tiles = ceil_div(a.kpad, 128);
-  const int N = a.kpad < 128 ? a.kpad : 128;
-  int tg = (512 - 32) / N;                        // taps whose accumulators fit in TMEM beside the bias columns
-  if (tg > a.taps) tg = a.taps;
-  prm.tap_groups = ceil_div(a.taps, tg);
-  prm.tg = ceil_div(a.taps, prm.tap_groups);      // balance the groups (9 taps: 9 | 5+4 | 3+3+3)
-  int cols = prm.tg * N + 32, alloc = 32;
+  prm.kb = (a.kpad < 128 ? a.kpad : 128) / 32;
+  prm.tpm = prm.kb == 3 ? 1 : 4 / prm.kb;
+  if (prm.tpm > a.taps) prm.tpm = a.taps;
+  const int N = pad_to(a.n < 128 ? a.n : 128, 32);
+  int max_groups = 512 / N - 1;                   // one N-wide column block is kept for the bias group
+  if (max_groups > WG_MAX_GROUPS) max_groups = WG_MAX_GROUPS;
+  int groups_total = ceil_div(a.taps, prm.tpm);
+  prm.tap_ranges = ceil_div(groups_total, max_groups);
+  int groups_per_range = ceil_div(groups_total, prm.tap_ranges);
+  prm.taps_per_range = groups_per_range * prm.tpm;
+  prm.tap_ranges = ceil_div(a.taps, prm.taps_per_range);
+  int cols = (groups_per_range + 1) * N, alloc = 32;
   while (alloc < cols) alloc <<= 1;
   prm.tmem_cols = alloc;
   prm.num_tiles = ceil_div(P, 64);
-  const int base = prm.n_tiles * prm.k_tiles * prm.tap_groups;
+  const int base = prm.n_tiles * prm.k_tiles * prm.tap_ranges;
   int splits = ceil_div(kNumSMs, base);
   if (splits > prm.num_tiles) splits = prm.num_tiles;
   prm.tiles_per_split = ceil_div(prm.num_tiles, splits);

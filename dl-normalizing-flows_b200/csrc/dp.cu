@@ -1,17 +1,22 @@
 // Data-parallel plumbing (absent from the reference): an NCCL communicator owned by
-// the plan, used for (i) gradient-bucket all-reduce and (ii) the batch-norm statistic exchange that
-// turns every BN of the stack into a synchronised BN.  NCCL is resolved with dlopen at first use so
-// that the library loads on a box without it (single-GPU use never touches these symbols).
+// the plan, used for
+//   (i)  the gradient all-reduce: the flat gradient buffer is reduced in buckets of whole couplings
+//        on a side stream as soon as the backward of those couplings has been enqueued (couplings
+//        finish last -> first, and 93 of the 120 M parameters live in the last two groups, so most of
+//        the traffic overlaps the rest of the backward pass), and
+//   (ii) the batch-norm statistic exchange (per-channel double sums) that makes every BN of the stack
+//        a synchronised BN, issued in-stream between the producer and consumer kernels.
+// NCCL is resolved with dlopen at first use so that the library loads on a box without it.
 #include <dlfcn.h>
 #include <mutex>
 #include "kernels.h"
 
 namespace {
-// minimal NCCL ABI (nccl.h 2.2x): types and enum values are stable across 2.x
+// minimal NCCL ABI (nccl.h 2.x): types and enum values are stable across 2.x
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess_ = 0 };
-enum { ncclSum_ = 0 };
+enum { ncclSum_ = 0, ncclAvg_ = 4 };
 enum { ncclFloat32_ = 7, ncclFloat64_ = 8 };
 typedef int (*fn_GetUniqueId)(ncclUniqueId*);
 typedef int (*fn_CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
@@ -64,16 +69,45 @@ int need_nccl() {
   } while (0)
 }  // namespace
 
-// accessors implemented in runtime.cu (the plan struct is private to it)
 namespace rnvp {
-void** plan_comm_slot(rnvp_plan* p);
-void plan_set_ranks(rnvp_plan* p, int rank, int world);
-int plan_world(const rnvp_plan* p);
+DpState* plan_dp(rnvp_plan* p);              // runtime.cu (the plan struct is private to it)
+int plan_num_couplings(const rnvp_plan* p);
 
-int dp_allreduce_doubles(rnvp_plan* plan, double* buf, size_t n, cudaStream_t st) {
-  ncclComm_t comm = (ncclComm_t)*plan_comm_slot(plan);
-  RNVP_REQUIRE(comm != nullptr, "data-parallel communicator not initialised");
-  RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, ncclSum_, comm, st));
+int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st) {
+  RNVP_REQUIRE(dp->comm != nullptr, "data-parallel communicator not initialised");
+  RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, ncclSum_, (ncclComm_t)dp->comm, st));
+  return RNVP_OK;
+}
+
+static int launch_bucket(DpState* dp, int64_t begin, int64_t end, cudaStream_t main) {
+  if (end <= begin) return RNVP_OK;
+  RNVP_CUDA(cudaEventRecord(dp->ev_main, main));
+  RNVP_CUDA(cudaStreamWaitEvent(dp->comm_stream, dp->ev_main, 0));
+  RNVP_NCCL(g_nccl.AllReduce(dp->flat + begin, dp->flat + begin, (size_t)(end - begin), ncclFloat32_, ncclAvg_,
+                             (ncclComm_t)dp->comm, dp->comm_stream));
+  dp->launched = true;
+  return RNVP_OK;
+}
+
+int dp_coupling_done(DpState* dp, int ci, cudaStream_t main) {
+  if (dp->world <= 1 || dp->flat == nullptr) return RNVP_OK;
+  if (dp->pending_end < 0) dp->pending_end = dp->off[dp->n_cpl];
+  const int64_t begin = dp->off[ci];
+  if (dp->pending_end - begin >= dp->bucket_elems || ci == 0) {
+    RNVP_TRY(launch_bucket(dp, begin, dp->pending_end, main));
+    dp->pending_end = begin;
+  }
+  return RNVP_OK;
+}
+
+int dp_join(DpState* dp, cudaStream_t main) {
+  if (dp->world <= 1 || dp->flat == nullptr) return RNVP_OK;
+  if (dp->launched) {
+    RNVP_CUDA(cudaEventRecord(dp->ev_comm, dp->comm_stream));
+    RNVP_CUDA(cudaStreamWaitEvent(main, dp->ev_comm, 0));
+  }
+  dp->pending_end = -1;
+  dp->launched = false;
   return RNVP_OK;
 }
 }  // namespace rnvp
@@ -91,32 +125,61 @@ int rnvp_dp_unique_id(void* id128) {
 int rnvp_dp_init(rnvp_plan* plan, const void* id128, int rank, int world) {
   RNVP_REQUIRE(plan && id128 && world >= 1 && rank >= 0 && rank < world, "bad data-parallel arguments");
   RNVP_TRY(need_nccl());
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  RNVP_REQUIRE(dp->comm == nullptr, "data-parallel communicator already initialised");
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   ncclComm_t comm = nullptr;
   RNVP_NCCL(g_nccl.CommInitRank(&comm, world, id, rank));
-  *rnvp::plan_comm_slot(plan) = comm;
-  rnvp::plan_set_ranks(plan, rank, world);
+  dp->comm = comm;
+  dp->rank = rank;
+  dp->world = world;
+  RNVP_CUDA(cudaStreamCreateWithFlags(&dp->comm_stream, cudaStreamNonBlocking));
+  RNVP_CUDA(cudaEventCreateWithFlags(&dp->ev_main, cudaEventDisableTiming));
+  RNVP_CUDA(cudaEventCreateWithFlags(&dp->ev_comm, cudaEventDisableTiming));
+  return RNVP_OK;
+}
+
+int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets_host, int64_t bucket_elems) {
+  RNVP_REQUIRE(plan && flat && offsets_host, "null argument");
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  const int n = rnvp::plan_num_couplings(plan);
+  delete[] dp->off;
+  dp->off = new int64_t[n + 1];
+  for (int i = 0; i <= n; ++i) dp->off[i] = offsets_host[i];
+  dp->n_cpl = n;
+  dp->flat = flat;
+  if (bucket_elems > 0) dp->bucket_elems = bucket_elems;
+  dp->pending_end = -1;
   return RNVP_OK;
 }
 
 int rnvp_dp_finalize(rnvp_plan* plan) {
   if (!plan) return RNVP_OK;
-  void** slot = rnvp::plan_comm_slot(plan);
-  if (*slot) {
-    RNVP_NCCL(g_nccl.CommDestroy((ncclComm_t)*slot));
-    *slot = nullptr;
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  if (dp->comm) {
+    cudaStreamSynchronize(dp->comm_stream);
+    RNVP_NCCL(g_nccl.CommDestroy((ncclComm_t)dp->comm));
+    dp->comm = nullptr;
+    cudaStreamDestroy(dp->comm_stream);
+    cudaEventDestroy(dp->ev_main);
+    cudaEventDestroy(dp->ev_comm);
+    dp->comm_stream = nullptr;
   }
-  rnvp::plan_set_ranks(plan, 0, 1);
+  delete[] dp->off;
+  dp->off = nullptr;
+  dp->flat = nullptr;
+  dp->rank = 0;
+  dp->world = 1;
   return RNVP_OK;
 }
 
 int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream) {
   RNVP_REQUIRE(plan, "null plan");
-  if (rnvp::plan_world(plan) <= 1 || n == 0) return RNVP_OK;
-  ncclComm_t comm = (ncclComm_t)*rnvp::plan_comm_slot(plan);
-  RNVP_REQUIRE(comm != nullptr, "data-parallel communicator not initialised");
-  RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat32_, ncclSum_, comm, (cudaStream_t)stream));
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  if (dp->world <= 1 || n == 0) return RNVP_OK;
+  RNVP_REQUIRE(dp->comm != nullptr, "data-parallel communicator not initialised");
+  RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat32_, ncclSum_, (ncclComm_t)dp->comm, (cudaStream_t)stream));
   return RNVP_OK;
 }
 

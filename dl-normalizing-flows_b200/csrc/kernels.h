@@ -103,6 +103,25 @@ int k_sumsq(const Seg* segs_dev, int nsegs, double* acc, cudaStream_t st);      
 int k_sumsq_finish(const double* acc, float* out, cudaStream_t st);
 int k_sumsq_bwd(const Seg* segs_dev, int nsegs, const float* dws_dev, cudaStream_t st);   // g += 2*p*dws
 
+// ---- data parallel state owned by a plan (dp.cu) -------------------------------------
+struct DpState {
+  void* comm = nullptr;              // ncclComm_t
+  int rank = 0, world = 1;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+  float* flat = nullptr;             // flat gradient buffer (all couplings, forward order)
+  int64_t* off = nullptr;            // host array: n_cpl + 1 element offsets into `flat`
+  int n_cpl = 0;
+  int64_t pending_end = -1;          // end of the not-yet-reduced contiguous range
+  int64_t bucket_elems = 1 << 20;    // reduce when at least this many elements are pending
+  bool launched = false;
+};
+int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st);
+// called after the backward of coupling `ci` was enqueued on `main` (couplings finish last -> first)
+int dp_coupling_done(DpState* dp, int ci, cudaStream_t main);
+// make `main` wait for every gradient bucket launched during this backward
+int dp_join(DpState* dp, cudaStream_t main);
+
 // ---- convolutions -------------------------------------------------------------------
 struct ConvArgs {
   const float* x;      // [B,S,S,kpad] activated input

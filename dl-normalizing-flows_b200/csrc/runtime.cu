@@ -13,7 +13,6 @@
 namespace rnvp {
 const char* get_error();
 unsigned long long launch_count();
-int dp_allreduce_doubles(rnvp_plan* plan, double* buf, size_t n, cudaStream_t st);   // dp.cu
 
 // ---- per-kernel-class event timing --------------------------------------------------
 struct ProfRec { int kind, S, taps, cin, cout; cudaEvent_t a, b; };
@@ -119,8 +118,8 @@ struct rnvp_plan {
   bool bound = false;
   bool single = false;               // one stand-alone coupling (rnvp_plan_create_single)
   // data parallel
-  void* comm = nullptr;
-  int rank = 0, world = 1;
+  DpState dp;
+  int& world = dp.world;
   // forward bookkeeping for backward
   int saved_batch = -1;
   int saved_coupling = -1;           // >=0: a stand-alone coupling forward was saved
@@ -369,7 +368,7 @@ int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* str
 }
 
 int sync_stats(const Ctx& c, double* buf, size_t n) {
-  if (c.p->world > 1) return dp_allreduce_doubles(c.p, buf, n, c.st);
+  if (c.p->world > 1) return dp_allreduce_doubles(&c.p->dp, buf, n, c.st);
   return RNVP_OK;
 }
 
@@ -908,6 +907,7 @@ int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scal
     for (int i = 0; i < n; ++i, --ci) {
       float* dx = f.G[k ^= 1];
       RNVP_TRY(coupling_backward(c, ci, dcur, dll, dx));
+      if (p->world > 1) RNVP_TRY(dp_coupling_done(&p->dp, ci, c.st));   // overlap: reduce finished buckets
       dcur = dx;
     }
     return RNVP_OK;
@@ -929,6 +929,7 @@ int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scal
     RNVP_TRY(run_group(3));
   }
   if (dx_nchw) RNVP_TRY(k_nhwc_to_nchw(dcur, dx_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  if (p->world > 1) RNVP_TRY(dp_join(&p->dp, c.st));
   p->saved_batch = -1;
   return RNVP_OK;
 }
@@ -1169,7 +1170,6 @@ int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias, i
 }  // extern "C"
 
 namespace rnvp {
-void** plan_comm_slot(rnvp_plan* p) { return &p->comm; }
-void plan_set_ranks(rnvp_plan* p, int rank, int world) { p->rank = rank; p->world = world; }
-int plan_world(const rnvp_plan* p) { return p->world; }
+DpState* plan_dp(rnvp_plan* p) { return &p->dp; }
+int plan_num_couplings(const rnvp_plan* p) { return (int)p->cpl.size(); }
 }  // namespace rnvp

@@ -68,6 +68,7 @@ def _load():
         "rnvp_conv_wgrad": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "rnvp_dp_unique_id": (i32, [vp]),
         "rnvp_dp_init": (i32, [vp, vp, i32, i32]),
+        "rnvp_dp_set_grad_layout": (i32, [vp, vp, C.POINTER(C.c_int64), C.c_int64]),
         "rnvp_dp_finalize": (i32, [vp]),
         "rnvp_dp_allreduce": (i32, [vp, vp, sz, vp]),
     }

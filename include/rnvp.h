@@ -196,6 +196,12 @@ int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias,
 /* 128-byte NCCL unique id, created on rank 0 and shipped by the caller      */
 int rnvp_dp_unique_id(void* id128_host);
 int rnvp_dp_init(rnvp_plan* plan, const void* id128_host, int rank, int world);
+/* Tell the plan where the gradients live so that rnvp_flow_backward can all-reduce (average) them in
+ * buckets while the rest of the backward runs: `flat` is the contiguous fp32 buffer that the bound
+ * grads point into (couplings in forward order), offsets_host[i] .. offsets_host[i+1] the element
+ * range of coupling i (num_couplings + 1 entries).  Buckets are whole couplings, at least
+ * bucket_elems elements (0 = default 1 Mi).                                                  */
+int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets_host, int64_t bucket_elems);
 int rnvp_dp_finalize(rnvp_plan* plan);
 /* sum-all-reduce `n` floats in place on `stream` (gradient buckets)         */
 int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream);

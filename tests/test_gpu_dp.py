@@ -1,0 +1,97 @@
+"""-m gpu: 2-rank NCCL data parallel == single process on the concatenated batch (needs >= 2 GPUs)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    import importlib
+    import warnings
+    warnings.filterwarnings("ignore")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pkg = importlib.import_module("dl-normalizing-flows_b200")
+    import realnvp_oracle as O
+    import rnvp_dp
+    ch, img, base, R, L, B = 3, 32, 32, 1, 3, 8
+    st0 = O.random_state(ch, img, base, R, L, seed=2)
+    g = torch.Generator().manual_seed(9)
+    x_all = torch.randn(B, ch, img, img, generator=g)
+    prior = torch.distributions.Normal(torch.tensor(0., device=dev), torch.tensor(1., device=dev))
+
+    def make():
+        m = pkg.RealNVP(ch, img, prior, pkg.Hyperparameters(base, R, True, True, True, True), num_scales=L)
+        m.load_state_dict(st0)
+        m = m.to(dev)
+        m.set_math("fp32")
+        m.train()
+        return m
+
+    # single-process reference on the full batch (every rank computes it; rank 0 reports)
+    ref = make()
+    ll, ws = ref(x_all.to(dev))
+    (-(ll).mean() + 5e-5 * ws).backward()
+    ref_grads = {k: p.grad.clone() for k, p in ref.named_parameters() if p.grad is not None}
+    ref_stats = {k: v.clone() for k, v in ref.state_dict().items() if k.endswith("running_var")}
+
+    m = make()
+    if rank != 0:                       # the wrapper must broadcast rank 0's weights
+        with torch.no_grad():
+            for p in m.parameters():
+                p.add_(0.01)
+    dp = rnvp_dp.DataParallel(m, bucket_elems=1 << 16)
+    b0, b1 = rnvp_dp.shard_batch(B, rank, world)
+    ll2, ws2 = dp(x_all[b0:b1].to(dev))
+    (-(ll2).mean() + 5e-5 * ws2).backward()
+    torch.cuda.synchronize()
+    err_ll = float((ll2 - ll[b0:b1]).abs().max() / ll.abs().max())
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    worst, wk = 0.0, None
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            continue
+        e = float((p.grad - ref_grads[k]).abs().max()) / max(float(ref_grads[k].abs().max()), 1e-3 * gmax)
+        if e > worst:
+            worst, wk = e, k
+    err_rv = max(float((m.state_dict()[k] - v).abs().max() / v.abs().max()) for k, v in ref_stats.items())
+    ret[rank] = (err_ll, worst, wk, err_rv, len(dp.buckets))
+    dp.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_equals_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    for r in range(2):
+        err_ll, worst, wk, err_rv, nb = ret[r]
+        assert err_ll < 1e-5, (r, err_ll)
+        assert worst < 5e-3, (r, worst, wk)
+        assert err_rv < 1e-4, (r, err_rv)
+        assert nb >= 2

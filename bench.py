@@ -242,10 +242,17 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def note(msg):
+        if os.environ.get("RNVP_BENCH_VERBOSE"):
+            print(f"[rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     # ---- warm-up -------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    note("warm-up")
+    for i in range(max(args.warmup, 3)):
         step(dev_u8)
+        note(f"warm-up step {i} enqueued")
     barrier()
+    note("warm-up done")
 
     # ---- device-resident timing -------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -287,14 +294,17 @@ def run_b200(args):
     roof = None
     classes = []
     by_kind = {}
-    if rank == 0 and not args.no_prof:
+    nprof = 2
+    if not args.no_prof:
+        # every rank runs the profiled steps (under data parallelism a step is a collective)
         cabi.lib.rnvp_prof_enable(1)
-        nprof = 2
         for _ in range(nprof):
             step(dev_u8)
         rows = (C.c_double * (7 * 512))()
         n = cabi.lib.rnvp_prof_collect(rows, 512)
         cabi.lib.rnvp_prof_enable(0)
+        barrier()
+    if rank == 0 and not args.no_prof:
         peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -368,6 +378,10 @@ def run_b200(args):
 
 def main():
     args = parse()
+    wd = int(os.environ.get("RNVP_BENCH_WATCHDOG", "0"))
+    if wd:
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True)
     if args.impl == "reference":
         run_reference(args)
     else:

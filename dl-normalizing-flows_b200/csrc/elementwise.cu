@@ -348,7 +348,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     float4* dx, int accumulate, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
-                                    float* dbeta) {
+                                    float* dbeta, float inv_world) {
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -359,8 +359,10 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
     s_mean[c] = save[c];
     s_rstd[c] = rstd;
     if (blockIdx.x == 0) {
-      dbeta[c] += (float)sums2[c];
-      dgamma[c] += (float)sums2[C + c];
+      // sums2 holds GLOBAL sums under data parallelism; every rank adds its 1/world share so that the
+      // gradient average over ranks is the global gradient
+      dbeta[c] += (float)sums2[c] * inv_world;
+      dgamma[c] += (float)sums2[C + c] * inv_world;
     }
   }
   __syncthreads();
@@ -384,12 +386,12 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, cudaStream_t st) {
+                   float* dgamma, float* dbeta, float inv_world, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
   bn_bwd_apply_kernel<<<grid_for(n4, kThreads * 2), kThreads, 5 * C * sizeof(float), st>>>(
       (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld, save, sums2, count, gamma,
-      dgamma, dbeta);
+      dgamma, dbeta, inv_world);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -802,14 +804,14 @@ __global__ void cpl_in_bwd_b_kernel(const float* __restrict__ dh0, const float* 
                                     CplGeom g, const float* __restrict__ save,
                                     const double* __restrict__ sums3, double count,
                                     const float* __restrict__ gamma, float* dgamma, float* dbeta,
-                                    float* __restrict__ dx) {
+                                    float* __restrict__ dx, float inv_world) {
   __shared__ float s_m1[kMaxCio], s_m2[kMaxCio];
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
     s_m1[c] = (float)(sums3[c] / count);
     s_m2[c] = (float)(sums3[g.cio + c] / count);
     if (blockIdx.x == 0) {
-      dbeta[c] += (float)sums3[c];
-      dgamma[c] += (float)sums3[g.cio + c];
+      dbeta[c] += (float)sums3[c] * inv_world;
+      dgamma[c] += (float)sums3[g.cio + c] * inv_world;
     }
   }
   __syncthreads();
@@ -834,10 +836,10 @@ __global__ void cpl_in_bwd_b_kernel(const float* __restrict__ dh0, const float* 
 }
 int k_cpl_in_bwd_b(const float* dh0, const float* x, const float* dxdir, const float* dy, CplGeom g,
                    const float* save, const double* sums3, double count, const float* gamma, float* dgamma,
-                   float* dbeta, float* dx, cudaStream_t st) {
+                   float* dbeta, float* dx, float inv_world, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   cpl_in_bwd_b_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      dh0, x, dxdir, dy, g, save, sums3, count, gamma, dgamma, dbeta, dx);
+      dh0, x, dxdir, dy, g, save, sums3, count, gamma, dgamma, dbeta, dx, inv_world);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

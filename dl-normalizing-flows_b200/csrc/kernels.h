@@ -40,7 +40,7 @@ int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C,
 // dx (= or +=) gamma*rstd*(gm - m1 - xhat*m2); block 0 adds dgamma/dbeta
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, cudaStream_t st);
+                   float* dgamma, float* dbeta, float inv_world, cudaStream_t st);
 
 // ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
@@ -66,7 +66,7 @@ int k_cpl_in_bwd_a(const float* dh0, const float* x, CplGeom g, const float* sav
                    cudaStream_t st);
 int k_cpl_in_bwd_b(const float* dh0, const float* x, const float* dxdir, const float* dy, CplGeom g,
                    const float* save, const double* sums3, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float* dx, cudaStream_t st);
+                   float* dgamma, float* dbeta, float* dx, float inv_world, cudaStream_t st);
 
 // ---- prior, per-sample sums ---------------------------------------------------------
 int k_prior_ll(const float* z, int B, int n, float loc, float scale, double* acc, cudaStream_t st);

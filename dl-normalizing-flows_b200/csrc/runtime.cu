@@ -467,7 +467,8 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
     RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
     return k_bn_bwd_apply(g, x, out ? out : g, accumulate, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
-                          P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b), c.st);
+                          P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b),
+                          1.0f / p->world, c.st);
   };
   const ConvDesc* cv = d.convs.data();
   const ConvDesc& oc = cv[2 + 4 * R];
@@ -582,7 +583,8 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
   RNVP_TRY(k_cpl_in_bwd_a(dh0, x, g, c.save(d.save_in), c.sb(d.sb_in), c.st));
   RNVP_TRY(sync_stats(c, c.sb(d.sb_in), 2 * d.cio));
   RNVP_TRY(k_cpl_in_bwd_b(dh0, x, dxdir, dy, g, c.save(d.save_in), c.sb(d.sb_in), count,
-                          P_<float>(p, d, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_B), dx, c.st));
+                          P_<float>(p, d, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_B), dx,
+                          1.0f / p->world, c.st));
   RNVP_TRY(k_weightnorm_bwd(p->d_jobs + d.job0, (int)d.convs.size(), p->max_cout, c.weights(), c.dw(), c.st));
   return RNVP_OK;
 }

@@ -171,14 +171,19 @@ def run_reference(args):
 # the B200 path
 # ------------------------------------------------------------------------------------------
 def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
-    """Algorithmic traffic of one conv-class launch: every operand once (fp32 NHWC, padded rows)."""
+    """Algorithmic traffic / flops of one profiled launch class (fp32 NHWC, every operand once)."""
     pad = lambda v, m: (v + m - 1) // m * m
     P = B * S * S
     if kind in (0, 1):          # conv / dgrad: read input rows, write output rows, read weights
         byt = 4 * (P * pad(cin, 32) + P * cout + taps * pad(cout, 16) * pad(cin, 32))
-    else:                       # wgrad: read x rows and dy rows, write dw
+        flops = 2.0 * P * cin * cout * taps
+    elif kind == 2:             # wgrad: read x rows and dy rows, write dw
         byt = 4 * (P * pad(cin, 32) + P * pad(cout, 32) + taps * pad(cout, 16) * pad(cin, 32))
-    flops = 2.0 * P * cin * cout * taps
+        flops = 2.0 * P * cin * cout * taps
+    elif kind == 3:             # bn+relu apply: read x, write h
+        byt, flops = 4 * 2 * P * cin, 0.0
+    else:                       # bn backward = reduce (read g, x; write g*mask) + apply (read g, x; write dx)
+        byt, flops = 4 * 6 * P * cin, 0.0
     return byt, flops
 
 
@@ -324,7 +329,7 @@ def run_b200(args):
             by_kind[names[r["kind"]]] = by_kind.get(names[r["kind"]], 0.0) + r["ms"] / nprof
         if classes:
             top = classes[0]
-            if top["kind"] in (0, 1, 2):
+            if True:
                 byt, fl = conv_alg_bytes_and_flops(top["kind"], top["S"], top["taps"], top["cin"], top["cout"], B)
                 dur = top["ms"] / top["launches"] / 1e3
                 gbs, tfs = byt / dur / 1e9, fl / dur / 1e12
@@ -336,7 +341,9 @@ def run_b200(args):
                 else:
                     roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                             "frac": tfs / peaks["bf16_tflops"], "traffic": None}
-                roof["kernel"] = f"{names[top['kind']]}_{args.math} S={top['S']} {int(top['taps'] ** 0.5)}x{int(top['taps'] ** 0.5)} {top['cin']}->{top['cout']}"
+                roof["kernel"] = (f"{names[top['kind']]}_{args.math} S={top['S']} {int(top['taps'] ** 0.5)}x{int(top['taps'] ** 0.5)} "
+                                  f"{top['cin']}->{top['cout']}" if top["kind"] < 3 else
+                                  f"{names[top['kind']]} S={top['S']} C={top['cin']}")
                 roof["launches_per_step"] = top["launches"] // nprof
                 roof["avg_us"] = dur * 1e6
                 roof["share_of_profiled_kernel_time"] = top["ms"] / tot

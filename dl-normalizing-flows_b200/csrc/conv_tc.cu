@@ -58,6 +58,19 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -142,37 +155,50 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // forward / dgrad kernel (persistent)
 //
 // grid = min(#tiles, resident CTAs); every CTA walks tiles t = blockIdx.x, += gridDim.x.  The TMA
-// producer runs ahead across tile boundaries through a 4-stage smem ring; the accumulator is double
-// buffered in TMEM so the epilogue of tile i (TMEM -> registers -> bias/residual -> HBM, BN partial
-// sums) overlaps the loads and MMAs of tile i+1.
+// producer runs ahead across tile boundaries through an smem ring; the accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of tile i+1.
+// Epilogue (one warp per 32-row TMEM quarter, 32 columns at a time): the residual / skip tile is
+// prefetched by TMA into swizzled smem, the accumulator comes from TMEM, bias + residual are added in
+// registers (BN partial sums taken there), the result is written to swizzled smem and leaves through
+// a TMA store -- every global access of the epilogue is a full-line bulk transfer, and the tensor
+// map clips ragged row / channel counts.
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
+constexpr int EPI_BOX_BYTES = 32 * 128;  // 32 rows x 32 fp32
+constexpr int EPI_BYTES_PER_WARP = 3 * EPI_BOX_BYTES;   // 1 residual + 2 output staging boxes
+template <int BN> struct TcCfg { static constexpr int STAGES = BN == 32 ? 3 : (BN == 64 ? 2 : 4); };
 
 struct ConvTcParams {
   const float* bias;
-  const float* res;
-  float* y;
   double* stats;
-  int P, n, ldy, taps, kchunks;      // kchunks = kpad / 32
+  int has_res;
+  int P, n, taps, kchunks;           // kchunks = kpad / 32
   int S;
   int m_tiles, n_tiles;
 };
 
+// byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
+__device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
+                                                                   const __grid_constant__ CUtensorMap tmY,
+                                                                   const __grid_constant__ CUtensorMap tmR,
                                                                    const ConvTcParams prm) {
+  constexpr int STAGES = TcCfg<BN>::STAGES;
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[TC_STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[TC_STAGES];
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
+  __shared__ __align__(8) uint64_t res_bar[4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_sum[4][BN];
   __shared__ float red_sq[4][BN];
@@ -184,7 +210,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    for (int s = 0; s < TC_STAGES; ++s) {
+    prefetch_tmap(&tmY);
+    if (prm.has_res) prefetch_tmap(&tmR);
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -192,6 +220,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);        // one arrive per epilogue warp
     }
+    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
@@ -210,8 +239,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
         const int p0 = m_tile * 128;
         const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
         for (int it = 0; it < iters; ++it, ++it_glob) {
-          const int s = it_glob % TC_STAGES;
-          mbar_wait(&empty_bar[s], ((it_glob / TC_STAGES) & 1) ^ 1);
+          const int s = it_glob % STAGES;
+          mbar_wait(&empty_bar[s], ((it_glob / STAGES) & 1) ^ 1);
           const int tap = it / prm.kchunks, kc = it % prm.kchunks;
           int dy = 0, dx = 0;
           if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
@@ -233,8 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
         for (int it = 0; it < iters; ++it, ++it_glob) {
-          const int s = it_glob % TC_STAGES;
-          mbar_wait(&full_bar[s], (it_glob / TC_STAGES) & 1);
+          const int s = it_glob % STAGES;
+          mbar_wait(&full_bar[s], (it_glob / STAGES) & 1);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_TILE_BYTES;
@@ -250,76 +279,85 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;
+    uint8_t* res_buf = epi_smem + q * EPI_BYTES_PER_WARP;
+    uint8_t* out_buf = res_buf + EPI_BOX_BYTES;   // two boxes
     float acc_s[BN / 32], acc_q[BN / 32];         // per-lane column sums (column c0 + lane), n_tiles == 1
 #pragma unroll
     for (int i = 0; i < BN / 32; ++i) acc_s[i] = acc_q[i] = 0.f;
     const bool keep_stats = prm.stats != nullptr;
+    const int chunks_per_tile = min(BN / 32, ceil_div(prm.n, 32));   // column chunks that hold real channels
+    // residual prefetch of the first (tile, chunk) step of this warp
+    int step = 0;
+    if (prm.has_res && lane == 0 && (int)blockIdx.x < num_tiles) {
+      const int m_tile = blockIdx.x / prm.n_tiles, n0 = (blockIdx.x % prm.n_tiles) * BN;
+      mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
+      tma_load_2d(res_buf, &tmR, &res_bar[q], n0, m_tile * 128 + q * 32);
+    }
     int ti = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
       const int as = ti & 1;
       const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
-      const int p = m_tile * 128 + row;
-      const bool pvalid = p < prm.P;
-      float* yrow = prm.y + (int64_t)p * prm.ldy;
-      const float* rrow = prm.res ? prm.res + (int64_t)p * prm.ldy : nullptr;
+      const int prow0 = m_tile * 128 + q * 32;
+      const bool pvalid = prow0 + lane < prm.P;
       mbar_wait(&acc_full[as], (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int ci = 0; ci < BN / 32; ++ci) {
         const int c0 = ci * 32;
         const int nb = n0 + c0;
-        if (nb >= prm.n) break;
+        if (ci >= chunks_per_tile || nb >= prm.n) break;
         float v[32];
-        // residual first: its global-load latency overlaps the TMEM read
-        float r[32];
-        const bool full = nb + 32 <= prm.n;
-        if (rrow != nullptr && pvalid && full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 r4 = *reinterpret_cast<const float4*>(rrow + nb + j);
-            r[j] = r4.x; r[j + 1] = r4.y; r[j + 2] = r4.z; r[j + 3] = r4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0.f;
-        }
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
-        if (full) {
-          if (prm.bias) {
+        if (prm.bias) {
+          if (nb + 32 <= prm.n) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 b4 = *reinterpret_cast<const float4*>(prm.bias + nb + j);
               v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += (nb + j < prm.n) ? prm.bias[nb + j] : 0.f;
           }
+        }
+        if (prm.has_res) {
+          mbar_wait(&res_bar[q], step & 1);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += r[j];
-          if (pvalid) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(yrow + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 8; ++j) {
+            float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
+            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            int n = nb + j;
-            if (n < prm.n) {
-              v[j] += prm.bias ? prm.bias[n] : 0.f;
-              if (pvalid) {
-                if (rrow) v[j] += rrow[n];
-                yrow[n] = v[j];
-              }
-            } else {
-              v[j] = 0.f;
+          // the residual box is consumed: prefetch the one of the next step
+          __syncwarp();
+          if (lane == 0) {
+            int nt = t, nci = ci + 1;
+            if (nci >= chunks_per_tile || n0 + nci * 32 >= prm.n) { nt = t + gridDim.x; nci = 0; }
+            if (nt < num_tiles) {
+              const int nm = nt / prm.n_tiles, nn0 = (nt % prm.n_tiles) * BN;
+              mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
+              tma_load_2d(res_buf, &tmR, &res_bar[q], nn0 + nci * 32, nm * 128 + q * 32);
             }
           }
         }
+        // stage the 32x32 result box (swizzled) and hand it to TMA
+        uint8_t* ob = out_buf + (step & 1) * EPI_BOX_BYTES;
+        if (lane == 0) tma_store_wait_read<1>();          // the store that used this buffer two steps ago
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(ob + swz_off(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(ob, &tmY, nb, prow0);              // rows >= P and columns >= n are clipped by the map
+          tma_store_commit();
+        }
+        ++step;
         if (keep_stats) {
           float sq[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            if (!pvalid) v[j] = 0.f;
+            if (!pvalid || nb + j >= prm.n) v[j] = 0.f;
             sq[j] = v[j] * v[j];
           }
           float s1 = warp_transpose_sum(v, lane);
@@ -338,6 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
     }
+    if (lane == 0) tma_store_wait_all();
     if (keep_stats && prm.n_tiles == 1) {
 #pragma unroll
       for (int ci = 0; ci < BN / 32; ++ci) {
@@ -392,8 +431,8 @@ static int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64
                    box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu box %u %u %u)", (int)r, rank,
-              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2], box[0], box[1], box[2]);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dim0 %llu dim1 %llu box %u x %u)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
     return RNVP_ERR_CUDA;
   }
   return RNVP_OK;
@@ -422,14 +461,25 @@ bool tf32_supported(int S) {
   return pixel_box(S, 128, &a, &b, &c);
 }
 
+// 2-D map over a row-major [P, ld] fp32 tensor exposing `n` real columns, 32x32 boxes
+static int make_row_map(CUtensorMap* m, const float* base, int P, int n, int ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)n, (cuuint64_t)P};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  return encode_map(m, base, 2, dims, strides, box);
+}
+
 template <int BN>
 static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tmA, cudaStream_t st) {
-  CUtensorMap tmB;
+  CUtensorMap tmB, tmY, tmR;
   cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
   cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
-  constexpr int smem = TC_STAGES * (A_TILE_BYTES + BN * 128) + 1024;
+  RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
+  if (a.res) RNVP_TRY(make_row_map(&tmR, a.res, prm.P, a.n, a.ldy));
+  else tmR = tmY;
+  constexpr int smem = TcCfg<BN>::STAGES * (A_TILE_BYTES + BN * 128) + 4 * EPI_BYTES_PER_WARP + 1024;
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -443,7 +493,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
-  conv_fwd_tf32_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, prm);
+  conv_fwd_tf32_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, prm);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -460,8 +510,8 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   CUtensorMap tmA;
   RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
   ConvTcParams prm{};
-  prm.bias = a.bias; prm.res = a.res; prm.y = a.y; prm.stats = a.stats;
-  prm.P = P; prm.n = a.n; prm.ldy = a.ldy; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
+  prm.bias = a.bias; prm.has_res = a.res != nullptr; prm.stats = a.stats;
+  prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
   if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);
   if (a.n <= 64) return launch_fwd<64>(a, prm, tmA, st);

@@ -251,16 +251,29 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
     }
   }
   __syncthreads();
-  int l4 = ld >> 2;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(e % l4) * 4;
-    if (c >= C) continue;
-    float4 v = x[e];
-    v.x = maybe_round(fmaxf(fmaf(v.x, s_scale[c + 0], s_shift[c + 0]), 0.f), rnd);
-    v.y = maybe_round(fmaxf(fmaf(v.y, s_scale[c + 1], s_shift[c + 1]), 0.f), rnd);
-    v.z = maybe_round(fmaxf(fmaf(v.z, s_scale[c + 2], s_shift[c + 2]), 0.f), rnd);
-    v.w = maybe_round(fmaxf(fmaf(v.w, s_scale[c + 3], s_shift[c + 3]), 0.f), rnd);
-    h[e] = v;
+  const int l4 = ld >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;                       // independent 16-byte loads in flight per thread
+  for (int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e0 < n4; e0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t e = e0 + u * stride;
+      if (e < n4) v[u] = x[e];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t e = e0 + u * stride;
+      if (e >= n4) break;
+      int c = (int)(e % l4) * 4;
+      if (c >= C) continue;
+      float4 w = v[u];
+      w.x = maybe_round(fmaxf(fmaf(w.x, s_scale[c + 0], s_shift[c + 0]), 0.f), rnd);
+      w.y = maybe_round(fmaxf(fmaf(w.y, s_scale[c + 1], s_shift[c + 1]), 0.f), rnd);
+      w.z = maybe_round(fmaxf(fmaf(w.z, s_scale[c + 2], s_shift[c + 2]), 0.f), rnd);
+      w.w = maybe_round(fmaxf(fmaf(w.w, s_scale[c + 3], s_shift[c + 3]), 0.f), rnd);
+      h[e] = w;
+    }
   }
 }
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
@@ -269,7 +282,7 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, "bn_relu: C=%d ld=%d unsupported", C, ld);
   int64_t n4 = (int64_t)P * ld / 4;
-  bn_relu_kernel<<<grid_for(n4, kThreads * 2), kThreads, 2 * C * sizeof(float), st>>>(
+  bn_relu_kernel<<<grid_for(n4, kThreads * 4, kNumSMs * 8), kThreads, 2 * C * sizeof(float), st>>>(
       (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta, run_mean, run_var, save, mode,
       tf32_round);
   RNVP_LAUNCH_CHECK();
@@ -316,19 +329,35 @@ __global__ void bn_bwd_reduce_kernel(const float4* g, const float4* __restrict__
       scale[k] = save[2 * C + c + k];
       shift[k] = save[3 * C + c + k];
     }
-    for (int p = blockIdx.x * rows + row; p < P; p += gridDim.x * rows) {
-      int64_t e = (int64_t)p * (ld >> 2) + col;
-      float4 gv = g[e], xv = x[e];
-      float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    constexpr int U = 4;                     // rows in flight per thread (8 independent 16-byte loads)
+    const int pstride = gridDim.x * rows;
+    for (int p0 = blockIdx.x * rows + row; p0 < P; p0 += U * pstride) {
+      float4 gv[U], xv[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float hval = fmaf(xx[k], scale[k], shift[k]);
-        float m = hval > 0.f ? gg[k] : 0.f;
-        gg[k] = m;
-        acc[0][k] += m;
-        acc[1][k] += m * ((xx[k] - mean[k]) * rstd[k]);
+      for (int u = 0; u < U; ++u) {
+        int p = p0 + u * pstride;
+        if (p < P) {
+          int64_t e = (int64_t)p * (ld >> 2) + col;
+          gv[u] = g[e];
+          xv[u] = x[e];
+        }
       }
-      gm_out[e] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int p = p0 + u * pstride;
+        if (p >= P) break;
+        int64_t e = (int64_t)p * (ld >> 2) + col;
+        float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float hval = fmaf(xx[k], scale[k], shift[k]);
+          float m = hval > 0.f ? gg[k] : 0.f;
+          gg[k] = m;
+          acc[0][k] += m;
+          acc[1][k] += m * ((xx[k] - mean[k]) * rstd[k]);
+        }
+        gm_out[e] = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      }
     }
   }
   block_col_reduce<2>(acc, col, row, cols, rows, C, sums2, sm);
@@ -338,7 +367,7 @@ int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C,
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(C % 4 == 0 && C / 4 <= kThreads && ld >= C && ld % 4 == 0, "bn_bwd_reduce: unsupported C=%d", C);
   int rows = kThreads / (C / 4);
-  bn_bwd_reduce_kernel<<<grid_for(P, rows * 8, kNumSMs * 8), kThreads, 0, st>>>(
+  bn_bwd_reduce_kernel<<<grid_for(P, rows * 16, kNumSMs * 6), kThreads, 0, st>>>(
       (const float4*)g, (const float4*)x, (float4*)gm_out, P, C, ld, save, sums2);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
@@ -366,22 +395,37 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
     }
   }
   __syncthreads();
-  int l4 = ld >> 2;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(e % l4) * 4;
-    if (c >= C) continue;
-    float4 gv = gm[e], xv = x[e];
-    float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w}, r[4];
+  const int l4 = ld >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (int64_t e0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e0 < n4; e0 += U * stride) {
+    float4 gv[U], xv[U], ov[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float xh = (xx[k] - s_mean[c + k]) * s_rstd[c + k];
-      r[k] = s_a[c + k] * (gg[k] - s_m1[c + k] - xh * s_m2[c + k]);
+    for (int u = 0; u < U; ++u) {
+      int64_t e = e0 + u * stride;
+      if (e < n4) {
+        gv[u] = gm[e];
+        xv[u] = x[e];
+        if (accumulate) ov[u] = dx[e];
+      }
     }
-    if (accumulate) {
-      float4 o = dx[e];
-      r[0] += o.x; r[1] += o.y; r[2] += o.z; r[3] += o.w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int64_t e = e0 + u * stride;
+      if (e >= n4) break;
+      int c = (int)(e % l4) * 4;
+      if (c >= C) continue;
+      float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float xh = (xx[k] - s_mean[c + k]) * s_rstd[c + k];
+        r[k] = s_a[c + k] * (gg[k] - s_m1[c + k] - xh * s_m2[c + k]);
+      }
+      if (accumulate) {
+        r[0] += ov[u].x; r[1] += ov[u].y; r[2] += ov[u].z; r[3] += ov[u].w;
+      }
+      dx[e] = make_float4(r[0], r[1], r[2], r[3]);
     }
-    dx[e] = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
@@ -389,7 +433,7 @@ int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, i
                    float* dgamma, float* dbeta, float inv_world, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
-  bn_bwd_apply_kernel<<<grid_for(n4, kThreads * 2), kThreads, 5 * C * sizeof(float), st>>>(
+  bn_bwd_apply_kernel<<<grid_for(n4, kThreads * 4, kNumSMs * 8), kThreads, 5 * C * sizeof(float), st>>>(
       (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld, save, sums2, count, gamma,
       dgamma, dbeta, inv_world);
   RNVP_LAUNCH_CHECK();

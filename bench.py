@@ -188,6 +188,7 @@ def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
 
 
 def run_b200(args):
+    os.environ["NCCL_DEBUG"] = os.environ.get("RNVP_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("dl-normalizing-flows_b200")

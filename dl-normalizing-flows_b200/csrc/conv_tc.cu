@@ -532,10 +532,9 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
 // is one more M-group whose A operand is a constant all-ones tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
-constexpr int WG_A_STAGES = 4, WG_B_STAGES = 2;
-constexpr int WG_A_STAGE_BYTES = 4 * WG_BOX_BYTES;
-constexpr int WG_B_STAGE_BYTES = 4 * WG_BOX_BYTES;
-constexpr int WG_SMEM = WG_A_STAGES * WG_A_STAGE_BYTES + WG_B_STAGES * WG_B_STAGE_BYTES + WG_BOX_BYTES + 1024;
+constexpr int WG_MAX_STAGES = 8;              // ring depths are chosen per launch from the actual stage sizes
+constexpr int WG_RING_BYTES = 192 * 1024;     // A ring + B ring
+constexpr int WG_SMEM = WG_RING_BYTES + WG_BOX_BYTES + 1024;
 constexpr int WG_MAX_GROUPS = 16;
 
 struct WgradTcParams {
@@ -547,6 +546,7 @@ struct WgradTcParams {
   int tpm;                                  // taps packed into one M = 128 operand
   int tiles_per_split, num_tiles;           // 64-pixel tiles
   int tmem_cols;
+  int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
@@ -562,11 +562,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
                                                                      const WgradTcParams prm) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int WG_A_STAGES = prm.a_stages, WG_B_STAGES = prm.b_stages;
+  const int WG_A_STAGE_BYTES = prm.a_stage_bytes, WG_B_STAGE_BYTES = prm.b_stage_bytes;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = a_ring + WG_A_STAGES * WG_A_STAGE_BYTES;
-  float* ones = reinterpret_cast<float*>(b_ring + WG_B_STAGES * WG_B_STAGE_BYTES);
-  __shared__ __align__(8) uint64_t a_full[WG_A_STAGES], a_empty[WG_A_STAGES];
-  __shared__ __align__(8) uint64_t b_full[WG_B_STAGES], b_empty[WG_B_STAGES];
+  float* ones = reinterpret_cast<float*>(smem + WG_RING_BYTES);
+  __shared__ __align__(8) uint64_t a_full[WG_MAX_STAGES], a_empty[WG_MAX_STAGES];
+  __shared__ __align__(8) uint64_t b_full[WG_MAX_STAGES], b_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
 
@@ -742,6 +744,13 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   if (splits > prm.num_tiles) splits = prm.num_tiles;
   prm.tiles_per_split = ceil_div(prm.num_tiles, splits);
   splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
+  // A slots are always 4 boxes (the M = 128 operand addresses 4 boxes; unused ones stay idle smem and one
+  // of them holds the constant all-ones tile of the bias gradient); B stages hold the dy boxes
+  prm.a_stage_bytes = 4 * WG_BOX_BYTES;
+  prm.a_stages = 4;
+  prm.b_stage_bytes = (N / 32) * WG_BOX_BYTES;
+  prm.b_stages = (WG_RING_BYTES - prm.a_stages * prm.a_stage_bytes) / prm.b_stage_bytes;
+  if (prm.b_stages > 6) prm.b_stages = 6;
   static bool attr_set = false;
   if (!attr_set) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));

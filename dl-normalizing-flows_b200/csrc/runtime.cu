@@ -90,6 +90,8 @@ constexpr int kMaxR = 16;
 // float offsets (relative to the activation base of one coupling) of everything a coupling keeps
 struct CplAct {
   size_t h0, a[kMaxR + 1], u1[kMaxR], u2[kMaxR], skip, st, xprime, y, total;
+  size_t h[3 * kMaxR + 1];     // mode 2: normalised activations kept for the backward (one per BN)
+  bool keep_h;
 };
 
 struct Layout {
@@ -122,6 +124,7 @@ struct rnvp_plan {
   int& world = dp.world;
   // forward bookkeeping for backward
   int saved_batch = -1;
+  int saved_mode = 1;
   int saved_coupling = -1;           // >=0: a stand-alone coupling forward was saved
   std::vector<const float*> x_in;    // input of each coupling in the last training forward
 };
@@ -277,7 +280,7 @@ CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
   size_t Pn = (size_t)B * d.S * d.S, o = 0;
   auto take = [&](size_t n) { size_t r = o; o += align_up(n, 64); return r; };
   a.h0 = take(Pn * d.cin_pad);
-  if (mode == 1) {
+  if (mode >= 1) {
     for (int i = 0; i <= R; ++i) a.a[i] = take(Pn * d.ldD);
     for (int i = 0; i < R; ++i) { a.u1[i] = take(Pn * d.ldD); a.u2[i] = take(Pn * d.ldD); }
   } else {                               // inference: the trunk is updated in place
@@ -286,6 +289,9 @@ CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
     for (int i = 0; i < R; ++i) { a.u1[i] = uu; a.u2[i] = uu; }
   }
   a.skip = take(Pn * d.ldD);
+  a.keep_h = mode == 2;
+  if (mode == 2)
+    for (int i = 0; i < 3 * R + 1; ++i) a.h[i] = take(Pn * d.ldD);
   a.st = take(Pn * d.cst_pad);
   a.xprime = take(Pn * d.cio);
   a.y = take(Pn * d.C);
@@ -298,12 +304,12 @@ Layout compute_layout(const rnvp_plan* p, int B, int mode) {
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
   L.weights = take(p->weight_floats * 4);
-  L.dw = take(mode == 1 ? p->dw_floats * 4 : 0);
+  L.dw = take(mode >= 1 ? p->dw_floats * 4 : 0);
   L.accum = take((32 + 2 * (size_t)B) * 8);
   L.stats_f_bytes = p->stats_f_doubles * 8;
   L.stats_b_bytes = p->stats_b_doubles * 8;
   L.stats_f = take(L.stats_f_bytes);
-  L.stats_b = take(mode == 1 ? L.stats_b_bytes : 0);
+  L.stats_b = take(mode >= 1 ? L.stats_b_bytes : 0);
   L.saves = take(p->save_floats * 4);
   const rnvp_config& c = p->cfg;
   L.img = (size_t)B * c.channels * c.image_size * c.image_size;
@@ -317,17 +323,17 @@ Layout compute_layout(const rnvp_plan* p, int B, int mode) {
     const CouplingDesc& d = p->cpl[i];
     CplAct a = cpl_act(p, d, B, mode);
     L.cpl_act[i] = act_total * 4;
-    if (mode == 1) act_total += align_up(a.total, 256);
+    if (mode >= 1) act_total += align_up(a.total, 256);
     maxact = std::max(maxact, a.total);
     size_t Pn = (size_t)B * d.S * d.S;
     maxPD = std::max(maxPD, align_up(Pn * d.ldD, 64));
     maxaux = std::max(maxaux, align_up(Pn * d.cst_pad, 64) + align_up(Pn * d.cio, 64) + align_up(Pn * d.cin_pad, 64));
   }
-  if (mode != 1) act_total = align_up(maxact, 256);
+  if (mode < 1) act_total = align_up(maxact, 256);
   L.act = take(act_total * 4);
   for (auto& v : L.cpl_act) v += L.act;
   // scratch: H + (mode 1: T0, T1, DA, DO + dst/dxdir/dh0)
-  L.scratch = take((mode == 1 ? 5 * maxPD + maxaux : maxPD) * 4);
+  L.scratch = take((mode >= 1 ? 5 * maxPD + maxaux : maxPD) * 4);
   L.total = o;
   return L;
 }
@@ -406,10 +412,12 @@ int net_forward(const Ctx& c, int ci, int training) {
   float* H = c.scratch();
   const int rnd = p->math == RNVP_MATH_TF32;
   auto bias = [&](const ConvDesc& cv) { return cv.has_bias ? P_<float>(p, d, ci, cv.slot_bias) : nullptr; };
+  float* Hs = c.scratch();
   auto bn = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
     if (training) RNVP_TRY(sync_stats(c, c.sf(b.sf), 2 * b.C));
     ProfScope ps(PROF_BN, S, 0, b.C, b.C, c.st);
+    H = A.keep_h ? c.act(ci, A.h[bi]) : Hs;
     return k_bn_relu(x, H, Pn, b.C, ld, training ? c.sf(b.sf) : nullptr, count, P_<float>(p, d, ci, b.slot_w),
                      P_<float>(p, d, ci, b.slot_b), P_<float>(p, d, ci, b.slot_rm),
                      P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, rnd, c.st);
@@ -448,14 +456,20 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   size_t maxPD = 0;
   for (auto& q : p->cpl) maxPD = std::max(maxPD, align_up((size_t)c.B * q.S * q.S * q.ldD, 64));
   (void)PD;
-  float* H = c.scratch();
-  float* T0 = H + maxPD;
+  float* Hs = c.scratch();
+  float* H = Hs;
+  float* T0 = Hs + maxPD;
   float* T1 = T0 + maxPD;
   float* DA = T1 + maxPD;
   float* DO = DA + maxPD;
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
-  auto recompute = [&](int bi, const float* x) {
+  auto recompute = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
+    if (A.keep_h) {                      // mode 2: the forward kept relu(bn(x))
+      H = c.act(ci, A.h[bi]);
+      return RNVP_OK;
+    }
+    H = Hs;
     ProfScope ps(PROF_BN, S, 0, b.C, b.C, c.st);
     return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2,
                      p->math == RNVP_MATH_TF32, c.st);
@@ -777,7 +791,7 @@ int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* 
 
 size_t rnvp_plan_workspace_bytes(const rnvp_plan* p, int batch, int mode) {
   if (!p || batch <= 0) return 0;
-  return compute_layout(p, batch, mode ? 1 : 0).total;
+  return compute_layout(p, batch, mode < 0 ? 0 : (mode > 2 ? 2 : mode)).total;
 }
 
 // ---- the flow ------------------------------------------------------------------------
@@ -822,7 +836,8 @@ extern "C" {
 int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logdet, float* z_nchw,
                       float* weight_scale, int batch, int training, void* ws, size_t ws_bytes, void* stream) {
   Ctx c;
-  RNVP_TRY(make_ctx(p, batch, training ? 1 : 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(training >= 0 && training <= 2, "training must be 0, 1 or 2");
+  RNVP_TRY(make_ctx(p, batch, training, ws, ws_bytes, stream, &c));
   RNVP_REQUIRE(!p->single, "flow entry points need a plan made by rnvp_plan_create");
   const rnvp_config& cf = p->cfg;
   const int L = cf.num_scales;
@@ -877,14 +892,14 @@ int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logde
     }
     RNVP_TRY(k_nhwc_to_nchw(t, z_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
   }
-  if (training) p->saved_batch = batch;
+  if (training) { p->saved_batch = batch; p->saved_mode = training; }
   return RNVP_OK;
 }
 
 int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scale, float* dx_nchw, int batch, void* ws,
                        size_t ws_bytes, void* stream) {
   Ctx c;
-  RNVP_TRY(make_ctx(p, batch, 1, ws, ws_bytes, stream, &c));
+  RNVP_TRY(make_ctx(p, batch, p->saved_mode, ws, ws_bytes, stream, &c));
   RNVP_REQUIRE(!p->single, "flow entry points need a plan made by rnvp_plan_create");
   if (p->saved_batch != batch) {
     set_error("rnvp_flow_backward: no matching training forward (saved batch %d, got %d)", p->saved_batch, batch);
@@ -900,7 +915,7 @@ int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scal
   // gradient of the prior term wrt the final latent block
   {
     const CouplingDesc& last = p->cpl[ci];
-    CplAct A = cpl_act(p, last, batch, 1);
+    CplAct A = cpl_act(p, last, batch, c.mode);
     RNVP_TRY(k_prior_grad(c.act(ci, A.y), dll, f.G[0], 0, batch, (int)(f.n[L] / batch), cf.prior_loc,
                           cf.prior_scale, c.st));
   }
@@ -990,7 +1005,8 @@ int rnvp_flow_inverse(rnvp_plan* p, const float* z_nchw, float* x_nchw, int batc
 int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nchw, float* logJ_nchw, int batch,
                           int training, void* ws, size_t ws_bytes, void* stream) {
   Ctx c;
-  RNVP_TRY(make_ctx(p, batch, training ? 1 : 0, ws, ws_bytes, stream, &c));
+  RNVP_REQUIRE(training >= 0 && training <= 2, "training must be 0, 1 or 2");
+  RNVP_TRY(make_ctx(p, batch, training, ws, ws_bytes, stream, &c));
   RNVP_REQUIRE(ci >= 0 && ci < (int)p->cpl.size(), "coupling index %d out of range", ci);
   const CouplingDesc& d = p->cpl[ci];
   p->saved_batch = -1;
@@ -1003,7 +1019,7 @@ int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nc
   RNVP_TRY(coupling_forward(c, ci, f.T[0], f.T[1], logJ_nchw ? f.G[0] : nullptr, training));
   RNVP_TRY(k_nhwc_to_nchw(f.T[1], y_nchw, batch, d.C, d.S, d.S, c.st));
   if (logJ_nchw) RNVP_TRY(k_nhwc_to_nchw(f.G[0], logJ_nchw, batch, d.C, d.S, d.S, c.st));
-  if (training) { p->saved_coupling = ci; p->saved_batch = batch; }
+  if (training) { p->saved_coupling = ci; p->saved_batch = batch; p->saved_mode = training; }
   return RNVP_OK;
 }
 
@@ -1028,7 +1044,7 @@ int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nc
 int rnvp_coupling_backward(rnvp_plan* p, int ci, const float* dy_nchw, const float* dlogJ_nchw, float* dx_nchw,
                            int batch, void* ws, size_t ws_bytes, void* stream) {
   Ctx c;
-  RNVP_TRY(make_ctx(p, batch, 1, ws, ws_bytes, stream, &c));
+  RNVP_TRY(make_ctx(p, batch, p->saved_mode, ws, ws_bytes, stream, &c));
   if (p->saved_coupling != ci || p->saved_batch != batch) {
     set_error("rnvp_coupling_backward: no matching training forward of coupling %d at batch %d", ci, batch);
     return RNVP_ERR_STATE;

@@ -63,7 +63,8 @@ class Engine:
         self._trainable: List[nn.Parameter] = []
         self._flat_grad: Optional[torch.Tensor] = None
         self._views: List[torch.Tensor] = []
-        self._ws = {0: None, 1: None}
+        self._ws = {0: None, 1: None, 2: None}
+        self.train_mode = None              # None = pick 2 (keep activations) when memory allows, else 1
         self.dirty = True
         self.dp = None                      # set by rnvp_dp.DataParallel
 
@@ -161,11 +162,24 @@ class Engine:
                 _resolve(self.couplings[0], "scale") is not first:
             self.bind(device)
 
+    def pick_train_mode(self, batch: int, device: torch.device) -> int:
+        if self.train_mode is not None:
+            return self.train_mode
+        need2 = lib.rnvp_plan_workspace_bytes(self.handle, batch, 2)
+        ws = self._ws[2]
+        if ws is not None and ws.numel() >= need2 and ws.device == device:
+            return 2
+        free, _total = torch.cuda.mem_get_info(device)
+        held = sum(w.numel() for w in self._ws.values() if w is not None and w.device == device)
+        return 2 if need2 < 0.8 * (free + held) else 1
+
     def workspace(self, batch: int, mode: int, device: torch.device) -> torch.Tensor:
         need = lib.rnvp_plan_workspace_bytes(self.handle, batch, mode)
         ws = self._ws[mode]
         if ws is None or ws.numel() < need or ws.device != device:
             self._ws[mode] = None
+            if mode:                       # the two training layouts never coexist
+                self._ws[3 - mode] = None
             ws = torch.empty(need, dtype=torch.uint8, device=device)
             self._ws[mode] = ws
         return ws
@@ -206,14 +220,15 @@ class Engine:
         dev = x.device
         self.ensure_bound(dev)
         B = x.shape[0]
-        ws = self.workspace(B, 1 if training else 0, dev)
+        mode = self.pick_train_mode(B, dev) if training else 0
+        ws = self.workspace(B, mode, dev)
         ll = torch.empty(B, dtype=torch.float32, device=dev)
         logdet = torch.empty(B, dtype=torch.float32, device=dev)
         z = torch.empty_like(x) if want_z else None
         wsc = torch.empty((), dtype=torch.float32, device=dev) if want_ws else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.rnvp_flow_forward(self.handle, ptr(x), ptr(ll), ptr(logdet), ptr(z), ptr(wsc), B,
-                                    1 if training else 0, ptr(ws), ws.numel(), C.c_void_p(stream)))
+                                    mode, ptr(ws), ws.numel(), C.c_void_p(stream)))
         if training:
             torch._foreach_add_(self._nbt_all, 1)
         return ll, logdet, z, wsc, ws

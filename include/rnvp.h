@@ -101,7 +101,9 @@ int rnvp_plan_coupling_info(const rnvp_plan* plan, int i, char* name, int name_l
 int rnvp_plan_bind(rnvp_plan* plan, void* const* params_host, void* const* grads_host, void* stream);
 
 /* bytes of workspace the calls below need for batch B.
- * mode: 0 = inference forward / inverse, 1 = training forward + backward   */
+ * mode: 0 = inference forward / inverse,
+ *       1 = training forward + backward, lean (normalised activations are recomputed in the backward),
+ *       2 = training, fast (they are kept: ~1.9x the activation memory, 13 fewer passes per coupling) */
 size_t rnvp_plan_workspace_bytes(const rnvp_plan* plan, int batch, int mode);
 
 int rnvp_plan_set_math(rnvp_plan* plan, int math /* rnvp_math */);
@@ -113,8 +115,9 @@ int rnvp_plan_set_math(rnvp_plan* plan, int math /* rnvp_math */);
  *   logdet       (B)  log det only, may be NULL                 [out]
  *   z_nchw       (B,C,H,W) latent, may be NULL                  [out]
  *   weight_scale (1)  sum p^2 over trainable weight_g / scale, may be NULL [out]
- *   training     1: batch statistics, running stats updated, tensors saved in
- *                   the workspace for rnvp_flow_backward; 0: running statistics */
+ *   training     1 or 2: batch statistics, running stats updated, tensors saved in
+ *                   the workspace (laid out for that mode, see rnvp_plan_workspace_bytes) for
+ *                   rnvp_flow_backward; 0: running statistics                 */
 int rnvp_flow_forward(rnvp_plan* plan, const float* x_nchw, float* ll, float* logdet, float* z_nchw,
                       float* weight_scale, int batch, int training,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -255,3 +255,22 @@ def test_survey_operating_point(pkg, math, tol):
         ll_de, _ = m(x.to(DEV))
     print(f"[{math}] train ll {rel(ll_d, lp + ld):.2e} logdet {rel(ld_d, ld):.2e}; eval ll {rel(ll_de, ll_e):.2e}")
     assert rel(ll_de, ll_e) < (1e-5 if math == "fp32" else 5e-2)
+
+
+def test_lean_and_fast_training_modes_agree(pkg, golden_dir):
+    """Workspace mode 1 (recompute normalised activations) and mode 2 (keep them) are the same function."""
+    fix = torch.load(os.path.join(golden_dir, "small_64px_b2.pt"))
+    c = fix["config"]
+    st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
+    x = fix["x"].to(DEV)
+    out = {}
+    for mode in (1, 2):
+        m = build(pkg, c, st0, "fp32")
+        m.engine().train_mode = mode
+        m.train()
+        ll, ws = m(x)
+        (-(ll).mean() + 5e-5 * ws).backward()
+        out[mode] = (ll.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    assert torch.equal(out[1][0], out[2][0])
+    grel, worst, wk = compare_grads(out[2][1], {k: v.cpu() for k, v in out[1][1].items()})
+    assert grel < 1e-5 and worst < 1e-3, (grel, worst, wk)      # only atomic-order noise differs

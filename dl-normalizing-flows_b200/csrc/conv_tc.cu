@@ -172,6 +172,7 @@ template <int BN> struct TcCfg { static constexpr int STAGES = BN == 32 ? 3 : (B
 struct ConvTcParams {
   const float* bias;
   double* stats;
+  const float* bn_save;              // non-null: fused ReLU+BN backward epilogue (tmR maps the raw activations)
   int has_res;
   int P, n, taps, kchunks;           // kchunks = kpad / 32
   int S;
@@ -202,10 +203,18 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_sum[4][BN];
   __shared__ float red_sq[4][BN];
+  __shared__ __align__(16) float coef[2 * BN];  // (scale, shift) of the fused BN backward (n_tiles == 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = prm.taps * prm.kchunks;
   const int num_tiles = prm.m_tiles * prm.n_tiles;
+  const bool bnbwd = prm.bn_save != nullptr;
+  const bool coef_in_smem = bnbwd && prm.n_tiles == 1;          // else read through L1 from global
+  if (coef_in_smem)
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const int k = i / BN, cidx = i % BN;
+      coef[i] = cidx < prm.n ? prm.bn_save[(2 + k) * prm.n + cidx] : 0.f;
+    }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -320,12 +329,42 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
             for (int j = 0; j < 32; ++j) v[j] += (nb + j < prm.n) ? prm.bias[nb + j] : 0.f;
           }
         }
+        float w2[32];                              // second statistic of the fused BN backward
         if (prm.has_res) {
           mbar_wait(&res_bar[q], step & 1);
+          if (!bnbwd) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
-            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+            for (int j = 0; j < 8; ++j) {
+              float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
+              v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+            }
+          } else {
+            // v = dL/dh (dgrad result); the box holds the raw pre-BN activations x of this layer:
+            // gm = v * 1[x*scale+shift > 0]; second statistic sum gm*x (the consumer turns the pair
+            // (sum gm, sum gm*x) into sum gm*xhat = rstd*(sum gm*x - mean*sum gm) in double)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
+              float4 sc4, sh4;
+              const int cbase = nb + 4 * j;
+              if (coef_in_smem) {                   // n0 == 0: column index == channel index
+                sc4 = *reinterpret_cast<const float4*>(&coef[c0 + 4 * j]);
+                sh4 = *reinterpret_cast<const float4*>(&coef[BN + c0 + 4 * j]);
+              } else if (cbase + 4 <= prm.n) {
+                sc4 = __ldg(reinterpret_cast<const float4*>(prm.bn_save + 2 * prm.n + cbase));
+                sh4 = __ldg(reinterpret_cast<const float4*>(prm.bn_save + 3 * prm.n + cbase));
+              } else {
+                sc4 = sh4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              const float xr[4] = {r4.x, r4.y, r4.z, r4.w};
+              const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float gm = fmaf(xr[i], sc[i], sh[i]) > 0.f ? v[4 * j + i] : 0.f;
+                v[4 * j + i] = gm;
+                w2[4 * j + i] = gm * xr[i];
+              }
+            }
           }
           // the residual box is consumed: prefetch the one of the next step
           __syncwarp();
@@ -358,7 +397,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (!pvalid || nb + j >= prm.n) v[j] = 0.f;
-            sq[j] = v[j] * v[j];
+            sq[j] = bnbwd ? ((!pvalid || nb + j >= prm.n) ? 0.f : w2[j]) : v[j] * v[j];
           }
           float s1 = warp_transpose_sum(v, lane);
           float s2 = warp_transpose_sum(sq, lane);
@@ -477,7 +516,8 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
   RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
-  if (a.res) RNVP_TRY(make_row_map(&tmR, a.res, prm.P, a.n, a.ldy));
+  if (a.bn_x) RNVP_TRY(make_row_map(&tmR, a.bn_x, prm.P, a.n, a.ldy));
+  else if (a.res) RNVP_TRY(make_row_map(&tmR, a.res, prm.P, a.n, a.ldy));
   else tmR = tmY;
   constexpr int smem = TcCfg<BN>::STAGES * (A_TILE_BYTES + BN * 128) + 4 * EPI_BYTES_PER_WARP + 1024;
   static int ctas_per_sm = 0;
@@ -498,19 +538,29 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   return RNVP_OK;
 }
 
+bool conv_tf32_fusable(const ConvArgs& a) {
+  int bw, bh, bn;
+  return pixel_box(a.S, 128, &bw, &bh, &bn) && a.kpad % 32 == 0 && a.ldy % 4 == 0 && a.n <= 512;
+}
+
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   const int P = a.B * a.S * a.S;
   if (P == 0) return RNVP_OK;
   int bw, bh, bn;
-  if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0)
+  if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0) {
+    RNVP_REQUIRE(a.bn_x == nullptr, "fused BN-backward epilogue needs the tensor-core kernel");
     return k_conv_fwd_fp32(a, st);          // shapes the TMA box cannot express: CUDA-core kernel
+  }
+  RNVP_REQUIRE(a.bn_x == nullptr || (a.res == nullptr && a.bias == nullptr && a.n % 4 == 0 && a.bn_save && a.stats),
+               "fused BN-backward epilogue: needs stats and bn_save, excludes bias / residual, n % 4 == 0");
   RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "conv: taps=%d", a.taps);
   RNVP_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0,
                "conv operands must be 16-byte aligned");
   CUtensorMap tmA;
   RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
   ConvTcParams prm{};
-  prm.bias = a.bias; prm.has_res = a.res != nullptr; prm.stats = a.stats;
+  prm.bias = a.bias; prm.has_res = a.res != nullptr || a.bn_x != nullptr; prm.stats = a.stats;
+  prm.bn_save = a.bn_x ? a.bn_save : nullptr;
   prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
   if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);

@@ -377,21 +377,24 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     float4* dx, int accumulate, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
-                                    float* dbeta, float inv_world) {
+                                    float* dbeta, float inv_world, int raw_x_sums) {
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float rstd = save[C + c];
+    // second statistic: sum g*xhat, or (fused dgrad epilogue) sum g*x which maps to it linearly
+    double s1 = sums2[c];
+    double s2 = raw_x_sums ? (double)rstd * (sums2[C + c] - (double)save[c] * s1) : sums2[C + c];
     s_a[c] = gamma[c] * rstd;
-    s_m1[c] = (float)(sums2[c] / count);
-    s_m2[c] = (float)(sums2[C + c] / count);
+    s_m1[c] = (float)(s1 / count);
+    s_m2[c] = (float)(s2 / count);
     s_mean[c] = save[c];
     s_rstd[c] = rstd;
     if (blockIdx.x == 0) {
-      // sums2 holds GLOBAL sums under data parallelism; every rank adds its 1/world share so that the
+      // the sums are GLOBAL under data parallelism; every rank adds its 1/world share so that the
       // gradient average over ranks is the global gradient
-      dbeta[c] += (float)sums2[c] * inv_world;
-      dgamma[c] += (float)sums2[C + c] * inv_world;
+      dbeta[c] += (float)s1 * inv_world;
+      dgamma[c] += (float)s2 * inv_world;
     }
   }
   __syncthreads();
@@ -430,12 +433,12 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, cudaStream_t st) {
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
   bn_bwd_apply_kernel<<<grid_for(n4, kThreads * 4, kNumSMs * 8), kThreads, 5 * C * sizeof(float), st>>>(
       (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld, save, sums2, count, gamma,
-      dgamma, dbeta, inv_world);
+      dgamma, dbeta, inv_world, raw_x_sums);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

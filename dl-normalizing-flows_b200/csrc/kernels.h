@@ -37,10 +37,11 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
 // gm = g * 1[h>0] written to gm_out; sums2[0:C] += sum gm, sums2[C:2C] += sum gm*xhat
 int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C, int ld,
                     const float* save, double* sums2, cudaStream_t st);
-// dx (= or +=) gamma*rstd*(gm - m1 - xhat*m2); block 0 adds dgamma/dbeta
+// dx (= or +=) gamma*rstd*(gm - m1 - xhat*m2); block 0 adds dgamma/dbeta.  raw_x_sums: sums2[C:2C] holds
+// sum gm*x (fused dgrad epilogue) instead of sum gm*xhat
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, cudaStream_t st);
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st);
 
 // ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
@@ -131,9 +132,14 @@ struct ConvArgs {
   float* y;            // [P,ldy]
   double* stats;       // [2n] or null
   int B, S, kpad, n, npad, taps, ldy;
+  // fused ReLU+BN backward epilogue (dgrad only, tensor-core kernel only): y = acc * 1[bn_x*scale+shift > 0],
+  // stats = (sum y, sum y * xhat) with the coefficients of bn_save = (mean, rstd, scale, shift)[n]
+  const float* bn_x = nullptr;     // [P,ldy] raw pre-BN activations
+  const float* bn_save = nullptr;  // [4n]
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
+bool conv_tf32_fusable(const ConvArgs& a);   // true when k_conv_fwd_tf32 runs the tensor-core kernel for `a`
 struct WgradArgs {
   const float* x;      // [B,S,S,kpad]
   const float* dy;     // [P,lddy]

@@ -255,8 +255,8 @@ int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
     d.sf_out = sf; sf += 2 * d.cio;
     d.sb_cpl = sb; sb += 2 * d.cio + 2;
     d.sb_in = sb; sb += 2 * d.cio;
-    d.save_in = sv; sv += 4 * d.cio;
-    d.save_out = sv; sv += 2 * d.cio;
+    d.save_in = sv; sv += align_up(4 * d.cio, 4);
+    d.save_out = sv; sv += align_up(2 * d.cio, 4);        // keep every block 16-byte aligned (float4 reads)
     for (auto& b : d.bns) {
       b.sf = sf; sf += 2 * b.C;
       b.sb = sb; sb += 2 * b.C;
@@ -378,6 +378,20 @@ int sync_stats(const Ctx& c, double* buf, size_t n) {
   return RNVP_OK;
 }
 
+ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
+                   const float* bias, const float* res, double* stats) {
+  ConvArgs a{};
+  a.x = x;
+  a.w = c.weights() + (dgrad ? cv.wb_off : cv.wf_off);
+  a.bias = bias; a.res = res; a.y = y; a.stats = stats;
+  a.B = c.B; a.S = S;
+  a.kpad = dgrad ? cv.kpad_b : cv.kpad;
+  a.n = dgrad ? cv.cin : cv.cout;
+  a.npad = dgrad ? cv.npad_b : cv.npad;
+  a.taps = cv.taps; a.ldy = ldy;
+  return a;
+}
+
 int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
              const float* bias, const float* res, double* stats) {
   ProfScope ps(dgrad ? PROF_DGRAD : PROF_CONV, S, cv.taps, dgrad ? cv.cout : cv.cin, dgrad ? cv.cin : cv.cout, c.st);
@@ -475,22 +489,34 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
                      p->math == RNVP_MATH_TF32, c.st);
   };
   // BN+ReLU backward in place on g: g <- d(pre-BN input); out==nullptr: in place, else (+=) into out
-  auto bn_bwd = [&](int bi, float* g, const float* x, float* out, int accumulate) -> int {
+  // dgrad of `cv` applied to `dy`, then ReLU+BN backward through BN `bi` whose raw input was `x`:
+  // g <- d(pre-BN input) (in place, or (+=) into out).  With the tensor-core tier the mask and the two
+  // reductions ride in the dgrad epilogue; otherwise a separate reduce kernel does them.
+  auto dgrad_bn_bwd = [&](const ConvDesc& cvd, const float* dy, int bi, float* g, const float* x, float* out,
+                          int accumulate) -> int {
     const BnDesc& b = d.bns[bi];
+    ConvArgs a = conv_args(c, cvd, true, dy, S, g, ld, nullptr, nullptr, nullptr);
+    const bool fused = p->math == RNVP_MATH_TF32 && conv_tf32_fusable(a);
+    if (fused) {
+      ProfScope ps(PROF_DGRAD, S, cvd.taps, cvd.cout, cvd.cin, c.st);
+      a.bn_x = x; a.bn_save = c.save(b.save); a.stats = c.sb(b.sb);
+      RNVP_TRY(k_conv_fwd_tf32(a, c.st));
+    } else {
+      RNVP_TRY(run_conv(c, cvd, true, dy, S, g, ld, nullptr, nullptr, nullptr));
+    }
     ProfScope ps(PROF_BN_BWD, S, 0, b.C, b.C, c.st);
-    RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
+    if (!fused) RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
     RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
     return k_bn_bwd_apply(g, x, out ? out : g, accumulate, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
                           P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b),
-                          1.0f / p->world, c.st);
+                          1.0f / p->world, fused ? 1 : 0, c.st);
   };
   const ConvDesc* cv = d.convs.data();
   const ConvDesc& oc = cv[2 + 4 * R];
   // out_block: st = conv(relu(bn(skip)))
   RNVP_TRY(recompute(3 * R, c.act(ci, A.skip)));
   RNVP_TRY(run_wgrad(c, oc, H, dst, d.cst_pad, S, gbias(oc)));
-  RNVP_TRY(run_conv(c, oc, true, dst, S, T0, ld, nullptr, nullptr, nullptr));
-  RNVP_TRY(bn_bwd(3 * R, T0, c.act(ci, A.skip), DO, 0));
+  RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, T0, c.act(ci, A.skip), DO, 0));
   for (int i = R - 1; i >= 0; --i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
     float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
@@ -501,18 +527,15 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     // a_{i+1} = a_i + rb6(relu(bn3(u2)))
     RNVP_TRY(recompute(3 * i + 2, u2));
     RNVP_TRY(run_wgrad(c, *rb6, H, DA, ld, S, gbias(*rb6)));
-    RNVP_TRY(run_conv(c, *rb6, true, DA, S, T0, ld, nullptr, nullptr, nullptr));
-    RNVP_TRY(bn_bwd(3 * i + 2, T0, u2, nullptr, 0));
+    RNVP_TRY(dgrad_bn_bwd(*rb6, DA, 3 * i + 2, T0, u2, nullptr, 0));
     // u2 = rb3(relu(bn2(u1)))
     RNVP_TRY(recompute(3 * i + 1, u1));
     RNVP_TRY(run_wgrad(c, *rb3, H, T0, ld, S, nullptr));
-    RNVP_TRY(run_conv(c, *rb3, true, T0, S, T1, ld, nullptr, nullptr, nullptr));
-    RNVP_TRY(bn_bwd(3 * i + 1, T1, u1, nullptr, 0));
+    RNVP_TRY(dgrad_bn_bwd(*rb3, T0, 3 * i + 1, T1, u1, nullptr, 0));
     // u1 = rb0(relu(bn1(a_i)))
     RNVP_TRY(recompute(3 * i, ai));
     RNVP_TRY(run_wgrad(c, *rb0, H, T1, ld, S, nullptr));
-    RNVP_TRY(run_conv(c, *rb0, true, T1, S, T0, ld, nullptr, nullptr, nullptr));
-    RNVP_TRY(bn_bwd(3 * i, T0, ai, DA, 1));
+    RNVP_TRY(dgrad_bn_bwd(*rb0, T1, 3 * i, T0, ai, DA, 1));
   }
   // skip = in_skip(a0) (+...); a0 = in_block(h0)
   RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));

@@ -271,6 +271,6 @@ def test_lean_and_fast_training_modes_agree(pkg, golden_dir):
         ll, ws = m(x)
         (-(ll).mean() + 5e-5 * ws).backward()
         out[mode] = (ll.detach().clone(), {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
-    assert torch.equal(out[1][0], out[2][0])
+    assert rel(out[2][0], out[1][0]) < 1e-6        # double atomics: order-dependent in the last bit
     grel, worst, wk = compare_grads(out[2][1], {k: v.cpu() for k, v in out[1][1].items()})
     assert grel < 1e-5 and worst < 1e-3, (grel, worst, wk)      # only atomic-order noise differs

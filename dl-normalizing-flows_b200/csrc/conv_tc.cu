@@ -19,6 +19,7 @@
 // owns a (n-tile, k-tile, tap-group, pixel-range) slab, keeps up to 512 TMEM columns of partial dw
 // and flushes them with fp32 atomics.
 #include <cuda.h>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace rnvp {
@@ -167,6 +168,7 @@ constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 e
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
 constexpr int EPI_BOX_BYTES = 32 * 128;  // 32 rows x 32 fp32
 constexpr int EPI_BYTES_PER_WARP = 3 * EPI_BOX_BYTES;   // 1 residual + 2 output staging boxes
+constexpr int TC_MAX_STAGES = 4;
 template <int BN> struct TcCfg { static constexpr int STAGES = BN == 32 ? 3 : (BN == 64 ? 2 : 4); };
 
 struct ConvTcParams {
@@ -177,6 +179,7 @@ struct ConvTcParams {
   int P, n, taps, kchunks;           // kchunks = kpad / 32
   int S;
   int m_tiles, n_tiles;
+  int stages;                        // depth of the smem ring (<= TC_MAX_STAGES)
 };
 
 // byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
@@ -188,15 +191,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
                                                                    const __grid_constant__ CUtensorMap tmY,
                                                                    const __grid_constant__ CUtensorMap tmR,
                                                                    const ConvTcParams prm) {
-  constexpr int STAGES = TcCfg<BN>::STAGES;
+  const int STAGES = prm.stages;
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   __shared__ __align__(8) uint64_t res_bar[4];
@@ -519,7 +522,14 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   if (a.bn_x) RNVP_TRY(make_row_map(&tmR, a.bn_x, prm.P, a.n, a.ldy));
   else if (a.res) RNVP_TRY(make_row_map(&tmR, a.res, prm.P, a.n, a.ldy));
   else tmR = tmY;
-  constexpr int smem = TcCfg<BN>::STAGES * (A_TILE_BYTES + BN * 128) + 4 * EPI_BYTES_PER_WARP + 1024;
+  static int stages = 0;
+  if (!stages) {
+    stages = TcCfg<BN>::STAGES;
+    const char* e = getenv(BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
+    if (e && atoi(e) >= 1 && atoi(e) <= TC_MAX_STAGES) stages = atoi(e);
+  }
+  prm.stages = stages;
+  const int smem = stages * (A_TILE_BYTES + BN * 128) + 4 * EPI_BYTES_PER_WARP + 1024;
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -582,7 +592,7 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
 // is one more M-group whose A operand is a constant all-ones tile.
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
-constexpr int WG_MAX_STAGES = 8;              // ring depths are chosen per launch from the actual stage sizes
+constexpr int WG_MAX_STAGES = 16;              // ring depths are chosen per launch from the actual stage sizes
 constexpr int WG_RING_BYTES = 192 * 1024;     // A ring + B ring
 constexpr int WG_SMEM = WG_RING_BYTES + WG_BOX_BYTES + 1024;
 constexpr int WG_MAX_GROUPS = 16;
@@ -597,6 +607,8 @@ struct WgradTcParams {
   int tiles_per_split, num_tiles;           // 64-pixel tiles
   int tmem_cols;
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
+  int ring_bytes;                           // A ring + MMA slack + B ring; the all-ones box follows
+  int a_lbo;                                // byte stride between the 32-row groups of the A operand
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
@@ -615,8 +627,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   const int WG_A_STAGES = prm.a_stages, WG_B_STAGES = prm.b_stages;
   const int WG_A_STAGE_BYTES = prm.a_stage_bytes, WG_B_STAGE_BYTES = prm.b_stage_bytes;
   uint8_t* a_ring = smem;
-  uint8_t* b_ring = a_ring + WG_A_STAGES * WG_A_STAGE_BYTES;
-  float* ones = reinterpret_cast<float*>(smem + WG_RING_BYTES);
+  uint8_t* b_ring = smem + prm.ring_bytes - WG_B_STAGES * WG_B_STAGE_BYTES;
+  float* ones = reinterpret_cast<float*>(smem + prm.ring_bytes);
   __shared__ __align__(8) uint64_t a_full[WG_MAX_STAGES], a_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t b_full[WG_MAX_STAGES], b_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -710,7 +722,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
             const uint32_t a_addr = smem_u32(a_ring + as * WG_A_STAGE_BYTES);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)       // 8 x (K = 8 pixels = two 512-byte swizzle atoms)
-              umma_tf32(tmem_base + (uint32_t)(mg * N), make_desc(a_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32),
+              umma_tf32(tmem_base + (uint32_t)(mg * N), make_desc(a_addr + ks * 1024, (uint32_t)prm.a_lbo, 512, kLayoutSw128Base32),
                         make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
             umma_commit(&a_empty[as]);
           }
@@ -794,19 +806,57 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   if (splits > prm.num_tiles) splits = prm.num_tiles;
   prm.tiles_per_split = ceil_div(prm.num_tiles, splits);
   splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
-  // A slots are always 4 boxes (the M = 128 operand addresses 4 boxes; unused ones stay idle smem and one
-  // of them holds the constant all-ones tile of the bias gradient); B stages hold the dy boxes
-  prm.a_stage_bytes = 4 * WG_BOX_BYTES;
-  prm.a_stages = 4;
+  // smem plan.  The M = 128 A operand always addresses four 32-row groups.  With one real box per
+  // stage (<= 32 input channels, one tap) the four groups alias that box (LBO = 0) and a stage is 8 KB;
+  // otherwise a stage holds the real boxes and the trailing groups read into the following slots /
+  // slack (their accumulator rows are never read back).
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("RNVP_WG_VARIANT");      // debugging / A-B switch: 0 forces the 1-CTA layout
+    variant = e ? atoi(e) : 1;
+  }
+  const int a_boxes = prm.tpm * prm.kb > 4 ? 4 : prm.tpm * prm.kb;
   prm.b_stage_bytes = (N / 32) * WG_BOX_BYTES;
-  prm.b_stages = (WG_RING_BYTES - prm.a_stages * prm.a_stage_bytes) / prm.b_stage_bytes;
-  if (prm.b_stages > 6) prm.b_stages = 6;
+  bool two_ctas = false;
+  if (variant != 0 && a_boxes == 1) {
+    // compact: 8 KB A stages, the four groups alias the one box; small enough for two CTAs per SM
+    prm.a_stage_bytes = WG_BOX_BYTES;
+    prm.a_lbo = 0;
+    prm.a_stages = 4 * groups_per_range;
+    if (prm.a_stages > WG_MAX_STAGES) prm.a_stages = WG_MAX_STAGES;
+    prm.b_stages = 4;
+    prm.ring_bytes = prm.a_stages * prm.a_stage_bytes + prm.b_stages * prm.b_stage_bytes;
+    two_ctas = true;
+  } else {
+    prm.a_stage_bytes = 4 * WG_BOX_BYTES;           // full 4-box slots: trailing groups read idle smem
+    prm.a_lbo = WG_BOX_BYTES;
+    if (variant != 0 && prm.tmem_cols <= 256 && 2 * prm.a_stage_bytes + 2 * prm.b_stage_bytes <= 100 * 1024) {
+      prm.a_stages = 2;                             // two CTAs per SM hide the per-tile latency better
+      prm.b_stages = (100 * 1024 - 2 * prm.a_stage_bytes) / prm.b_stage_bytes;
+      if (prm.b_stages > 4) prm.b_stages = 4;
+      two_ctas = true;
+    } else {
+      prm.a_stages = 4;
+      prm.b_stages = (WG_RING_BYTES - prm.a_stages * prm.a_stage_bytes) / prm.b_stage_bytes;
+      if (prm.b_stages > 6) prm.b_stages = 6;
+    }
+    prm.ring_bytes = prm.a_stages * prm.a_stage_bytes + prm.b_stages * prm.b_stage_bytes;
+  }
+  prm.ring_bytes = (prm.ring_bytes + 1023) / 1024 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
     attr_set = true;
   }
-  conv_wgrad_tf32_kernel<<<dim3(base, splits), TC_THREADS, WG_SMEM, st>>>(tmDy, tmX, prm);
+  // with the compact layout two CTAs fit per SM: split the pixel range accordingly
+  const int dyn_smem = prm.ring_bytes + WG_BOX_BYTES + 1024;
+  if (two_ctas && 2 * (dyn_smem + 2048) <= 227 * 1024 && prm.tmem_cols <= 256) {
+    int splits2 = ceil_div(2 * kNumSMs, base);
+    if (splits2 > prm.num_tiles) splits2 = prm.num_tiles;
+    prm.tiles_per_split = ceil_div(prm.num_tiles, splits2);
+    splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
+  }
+  conv_wgrad_tf32_kernel<<<dim3(base, splits), TC_THREADS, dyn_smem, st>>>(tmDy, tmX, prm);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

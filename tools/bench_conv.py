@@ -15,7 +15,8 @@ pad = lambda v, m: (v + m - 1) // m * m
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def timeit(fn, n=20):
+def timeit(fn, n=None):
+    n = n or NITER
     for _ in range(3):
         fn(0)
     torch.cuda.synchronize()
@@ -29,8 +30,12 @@ def timeit(fn, n=20):
 
 
 print(f"{'shape':26s} {'kernel':10s} {'us':>8s} {'GB/s':>7s} {'TF/s':>6s} {'ideal_us':>8s}")
-for S, D, k in [(64, 32, 1), (64, 32, 3), (32, 64, 1), (32, 64, 3), (16, 128, 1), (16, 128, 3),
-                (8, 256, 1), (8, 256, 3), (4, 512, 1), (4, 512, 3)]:
+SHAPES = [(64, 32, 1), (64, 32, 3), (32, 64, 1), (32, 64, 3), (16, 128, 1), (16, 128, 3),
+          (8, 256, 1), (8, 256, 3), (4, 512, 1), (4, 512, 3)]
+if os.environ.get("SHAPES"):
+    SHAPES = [tuple(int(v) for v in t.split(",")) for t in os.environ["SHAPES"].split(";")]
+NITER = int(os.environ.get("NITER", "20"))
+for S, D, k in SHAPES:
     P = B * S * S
     kpad, npad = pad(D, 32), pad(D, 16)
     nset = max(2, min(6, int(300e6 // (P * D * 4)) + 1))

@@ -59,6 +59,24 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int pad_to(int a, int m) { return (a + m - 1) / m * m; }
 
+bool pdl_enabled();                     // RNVP_PDL=1 switches programmatic dependent launch on
+// launch `kernel` with the programmatic-stream-serialization attribute (plain launch when disabled)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int grid_for(int64_t work_items, int per_block, int max_blocks = kNumSMs * 16) {
   int64_t g = ceil_div64(work_items, per_block);
   if (g < 1) g = 1;
@@ -107,6 +125,12 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with the stream-serialization attribute may start
+// while its predecessor drains; it must call pdl_wait() before touching anything the predecessor wrote
+// (or writing anything it reads).  pdl_trigger() lets the successor begin launching early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // round-to-nearest fp32 -> tf32 (10-bit mantissa, low 13 bits cleared).  tcgen05 kind::tf32 simply
 // ignores the low bits (truncation, biased towards zero); tensors that exist only as conv operands are

@@ -213,11 +213,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   const int num_tiles = prm.m_tiles * prm.n_tiles;
   const bool bnbwd = prm.bn_save != nullptr;
   const bool coef_in_smem = bnbwd && prm.n_tiles == 1;          // else read through L1 from global
-  if (coef_in_smem)
-    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
-      const int k = i / BN, cidx = i % BN;
-      coef[i] = cidx < prm.n ? prm.bn_save[(2 + k) * prm.n + cidx] : 0.f;
-    }
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -236,6 +232,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
+  // everything above overlaps the tail of the previous kernel; from here on its results are needed
+  pdl_wait();
+  if (coef_in_smem)
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const int k = i / BN, cidx = i % BN;
+      coef[i] = cidx < prm.n ? prm.bn_save[(2 + k) * prm.n + cidx] : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -396,14 +399,36 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
         }
         ++step;
         if (keep_stats) {
-          float sq[32];
+          // per-channel sums straight from the staged (swizzled) box: lane c adds up column c over the 32
+          // rows of this warp -- every step reads one 128-byte row across the warp, conflict free.
+          // Rows past P were zero-filled by TMA in the inputs but carry the bias: mask them.
+          const int rows_valid = min(32, prm.P - prow0);
+          const int jc = lane >> 2, wc = (lane & 3) * 4;
+          float s1 = 0.f, s2 = 0.f;
+          if (!bnbwd) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              float val = *reinterpret_cast<const float*>(ob + swz_off(r, jc) + wc);
+              val = r < rows_valid ? val : 0.f;
+              s1 += val;
+              s2 = fmaf(val, val, s2);
+            }
+          } else {
+            // second statistic of the fused BN backward: sum gm * x, x = raw activations still in res_buf
+            // (the next residual prefetch targets the same buffer: it was issued after all lanes had
+            // read x into registers, so re-reading here would race -- use the register copy instead)
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              float val = *reinterpret_cast<const float*>(ob + swz_off(r, jc) + wc);
+              val = r < rows_valid ? val : 0.f;
+              s1 += val;
+            }
+            float wsum[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (!pvalid || nb + j >= prm.n) v[j] = 0.f;
-            sq[j] = bnbwd ? ((!pvalid || nb + j >= prm.n) ? 0.f : w2[j]) : v[j] * v[j];
+            for (int j = 0; j < 32; ++j) wsum[j] = pvalid ? w2[j] : 0.f;
+            s2 = warp_transpose_sum(wsum, lane);
           }
-          float s1 = warp_transpose_sum(v, lane);
-          float s2 = warp_transpose_sum(sq, lane);
+          if (nb + lane >= prm.n) { s1 = 0.f; s2 = 0.f; }
           if (prm.n_tiles == 1) {
             acc_s[ci] += s1;
             acc_q[ci] += s2;
@@ -543,7 +568,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
-  conv_fwd_tf32_kernel<BN><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmR, prm);
+  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -651,6 +676,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   const bool do_bias = prm.dbias != nullptr && kt == 0 && tr == 0;
   const uint32_t bias_col = (uint32_t)(groups * N);
 
+  pdl_trigger();
   for (int i = threadIdx.x; i < WG_BOX_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
   fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
   if (threadIdx.x == 0) {
@@ -662,6 +688,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_dyn(&tmem_base_slot, (uint32_t)prm.tmem_cols);
+  pdl_wait();                                // the prologue above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -856,7 +883,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
     prm.tiles_per_split = ceil_div(prm.num_tiles, splits2);
     splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
   }
-  conv_wgrad_tf32_kernel<<<dim3(base, splits), TC_THREADS, dyn_smem, st>>>(tmDy, tmX, prm);
+  RNVP_CUDA(launch_pdl(conv_wgrad_tf32_kernel, dim3(base, splits), dim3(TC_THREADS), (size_t)dyn_smem, st, tmDy, tmX, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

@@ -2,6 +2,7 @@
 // batch-norm apply / backward, the coupling maps with their per-sample log-det reductions,
 // the prior term and weight normalisation.  All fp32, NHWC, coalesced; reductions go through
 // warp shuffles -> shared memory -> one double atomic per block and channel.
+#include <cstdlib>
 #include "kernels.h"
 
 namespace rnvp {
@@ -14,6 +15,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;      // measured: no gain on this workload, so opt-in
+  }
+  return on != 0;
+}
 
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
@@ -226,6 +236,8 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
                                const double* __restrict__ sums, double count,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* run_mean, float* run_var, float* save, int mode, int rnd) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
   float* s_shift = sm + C;
@@ -282,9 +294,9 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, "bn_relu: C=%d ld=%d unsupported", C, ld);
   int64_t n4 = (int64_t)P * ld / 4;
-  bn_relu_kernel<<<grid_for(n4, kThreads * 4, kNumSMs * 8), kThreads, 2 * C * sizeof(float), st>>>(
-      (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta, run_mean, run_var, save, mode,
-      tf32_round);
+  RNVP_CUDA(launch_pdl(bn_relu_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
+                       2 * C * sizeof(float), st, (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta,
+                       run_mean, run_var, save, mode, tf32_round));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -378,6 +390,8 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
                                     float* dbeta, float inv_world, int raw_x_sums) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -436,9 +450,9 @@ int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, i
                    float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
-  bn_bwd_apply_kernel<<<grid_for(n4, kThreads * 4, kNumSMs * 8), kThreads, 5 * C * sizeof(float), st>>>(
-      (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld, save, sums2, count, gamma,
-      dgamma, dbeta, inv_world, raw_x_sums);
+  RNVP_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
+                       5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld,
+                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

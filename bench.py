@@ -326,6 +326,9 @@ def run_b200(args):
             classes.append(dict(kind=int(kind), S=int(S), taps=int(taps), cin=int(cin), cout=int(cout),
                                 launches=int(cnt), ms=tms))
         classes.sort(key=lambda r: -r["ms"])
+        if os.environ.get("RNVP_BENCH_CLASSES"):          # full per-class table (the JSON line keeps the top 16)
+            with open(os.environ["RNVP_BENCH_CLASSES"], "w") as f:
+                json.dump({"batch": B, "profiled_steps": nprof, "classes": classes}, f, indent=0)
         for r in classes:
             by_kind[names[r["kind"]]] = by_kind.get(names[r["kind"]], 0.0) + r["ms"] / nprof
         if classes:

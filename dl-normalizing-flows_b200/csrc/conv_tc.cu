@@ -180,6 +180,7 @@ struct ConvTcParams {
   int S;
   int m_tiles, n_tiles;
   int stages;                        // depth of the smem ring (<= TC_MAX_STAGES)
+  int rev;                           // walk the tiles from the last to the first (L2 reuse, see next_sweep_dir)
 };
 
 // byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     if (lane == 0) {
       const int hw = prm.S * prm.S;
       int it_glob = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x) {
+        const int t = prm.rev ? num_tiles - 1 - tt : tt;
         const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
         const int p0 = m_tile * 128;
         const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
@@ -304,12 +306,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     // residual prefetch of the first (tile, chunk) step of this warp
     int step = 0;
     if (prm.has_res && lane == 0 && (int)blockIdx.x < num_tiles) {
-      const int m_tile = blockIdx.x / prm.n_tiles, n0 = (blockIdx.x % prm.n_tiles) * BN;
+      const int t0 = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      const int m_tile = t0 / prm.n_tiles, n0 = (t0 % prm.n_tiles) * BN;
       mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
       tma_load_2d(res_buf, &tmR, &res_bar[q], n0, m_tile * 128 + q * 32);
     }
     int ti = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+    for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x, ++ti) {
+      const int t = prm.rev ? num_tiles - 1 - tt : tt;
       const int as = ti & 1;
       const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
       const int prow0 = m_tile * 128 + q * 32;
@@ -375,9 +379,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
           // the residual box is consumed: prefetch the one of the next step
           __syncwarp();
           if (lane == 0) {
-            int nt = t, nci = ci + 1;
-            if (nci >= chunks_per_tile || n0 + nci * 32 >= prm.n) { nt = t + gridDim.x; nci = 0; }
-            if (nt < num_tiles) {
+            int ntt = tt, nci = ci + 1;
+            if (nci >= chunks_per_tile || n0 + nci * 32 >= prm.n) { ntt = tt + gridDim.x; nci = 0; }
+            if (ntt < num_tiles) {
+              const int nt = prm.rev ? num_tiles - 1 - ntt : ntt;
               const int nm = nt / prm.n_tiles, nn0 = (nt % prm.n_tiles) * BN;
               mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
               tma_load_2d(res_buf, &tmR, &res_bar[q], nn0 + nci * 32, nm * 128 + q * 32);
@@ -558,10 +563,25 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int occ = 1;
+    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+    // resident CTAs per SM from the kernel's own footprint: shared memory (dynamic + static + 1 KB the
+    // driver reserves per CTA) against the 228 KB of an SM, registers against the 64 K file, TMEM columns
+    cudaFuncAttributes fa;
+    RNVP_CUDA(cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN>));
+    const int by_smem = (228 * 1024) / (smem + (int)fa.sharedSizeBytes + 1024);
+    const int by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (TC_THREADS / 32));
+    const int by_tmem = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+    int occ = 0;
     RNVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_tf32_kernel<BN>, TC_THREADS, smem));
-    int tmem_limit = 512 / (2 * BN < 32 ? 32 : 2 * BN);
-    ctas_per_sm = occ < 1 ? 1 : (occ > tmem_limit ? tmem_limit : occ);
+    int c = by_smem < by_regs ? by_smem : by_regs;
+    if (c > by_tmem) c = by_tmem;
+    ctas_per_sm = c < 1 ? 1 : c;
+    if (const char* e = getenv("RNVP_TC_CTAS")) { if (atoi(e) >= 1) ctas_per_sm = atoi(e); }
+    if (getenv("RNVP_DEBUG"))
+      fprintf(stderr, "[rnvp] conv_fwd_tf32<%d>: stages %d smem %d+%d regs %d -> by_smem %d by_regs %d by_tmem %d "
+              "(occupancy API %d) => %d CTAs/SM\n", BN, stages, smem, (int)fa.sharedSizeBytes, fa.numRegs, by_smem,
+              by_regs, by_tmem, occ, ctas_per_sm);
   }
   prm.m_tiles = ceil_div(prm.P, 128);
   prm.n_tiles = ceil_div(a.n, BN);
@@ -598,6 +618,7 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   prm.bn_save = a.bn_x ? a.bn_save : nullptr;
   prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
+  prm.rev = next_sweep_dir();
   if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);
   if (a.n <= 64) return launch_fwd<64>(a, prm, tmA, st);
   return launch_fwd<128>(a, prm, tmA, st);

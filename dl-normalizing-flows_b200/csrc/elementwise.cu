@@ -25,6 +25,21 @@ bool pdl_enabled() {
   return on != 0;
 }
 
+// Serpentine sweeps: consecutive kernels of a chain walk their tensors in opposite directions, so each
+// one starts on the part of its input that the previous kernel wrote last and that is still resident in
+// the 126 MB L2 (trunk tensors are 33-134 MB at batch 256).  RNVP_SERPENTINE=0 switches it off.
+int next_sweep_dir() {
+  static int on = -1;
+  static thread_local int dir = 0;
+  if (on < 0) {
+    const char* e = getenv("RNVP_SERPENTINE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on) return 0;
+  dir ^= 1;
+  return dir;
+}
+
 static unsigned long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
@@ -235,8 +250,7 @@ int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream
 __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict__ h, int64_t n4, int C, int ld,
                                const double* __restrict__ sums, double count,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                               float* run_mean, float* run_var, float* save, int mode, int rnd) {
-  pdl_trigger();
+                               float* run_mean, float* run_var, float* save, int mode, int rnd, int rev) {
   pdl_wait();
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
@@ -271,12 +285,13 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       int64_t e = e0 + u * stride;
-      if (e < n4) v[u] = x[e];
+      if (e < n4) v[u] = __ldcs(&x[rev ? n4 - 1 - e : e]);      // x is not read again before the backward
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       int64_t e = e0 + u * stride;
       if (e >= n4) break;
+      if (rev) e = n4 - 1 - e;
       int c = (int)(e % l4) * 4;
       if (c >= C) continue;
       float4 w = v[u];
@@ -287,6 +302,7 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
       h[e] = w;
     }
   }
+  pdl_trigger();
 }
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var, float* save, int mode,
@@ -296,7 +312,7 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_relu_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        2 * C * sizeof(float), st, (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta,
-                       run_mean, run_var, save, mode, tf32_round));
+                       run_mean, run_var, save, mode, tf32_round, next_sweep_dir()));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -389,8 +405,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     float4* dx, int accumulate, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
-                                    float* dbeta, float inv_world, int raw_x_sums) {
-  pdl_trigger();
+                                    float* dbeta, float inv_world, int raw_x_sums, int rev) {
   pdl_wait();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
@@ -421,8 +436,9 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
     for (int u = 0; u < U; ++u) {
       int64_t e = e0 + u * stride;
       if (e < n4) {
+        if (rev) e = n4 - 1 - e;
         gv[u] = gm[e];
-        xv[u] = x[e];
+        xv[u] = __ldcs(&x[e]);                 // last use of the saved activation
         if (accumulate) ov[u] = dx[e];
       }
     }
@@ -430,6 +446,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
     for (int u = 0; u < U; ++u) {
       int64_t e = e0 + u * stride;
       if (e >= n4) break;
+      if (rev) e = n4 - 1 - e;
       int c = (int)(e % l4) * 4;
       if (c >= C) continue;
       float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w}, r[4];
@@ -444,6 +461,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
       dx[e] = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
+  pdl_trigger();
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
@@ -452,7 +470,7 @@ int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, i
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld,
-                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums));
+                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, next_sweep_dir()));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

@@ -5,6 +5,9 @@
 
 namespace rnvp {
 
+// 0 / 1 alternating per call (see elementwise.cu): the direction in which the next bulk kernel sweeps
+int next_sweep_dir();
+
 // ---- layout (flow_realnvp.py:121-193), all NHWC ---------------------------------
 enum PermMode {
   PERM_SQUEEZE = 0,      // hi [B,2s,2s,C]            -> sq [B,s,s,4C]

@@ -214,7 +214,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   const int num_tiles = prm.m_tiles * prm.n_tiles;
   const bool bnbwd = prm.bn_save != nullptr;
   const bool coef_in_smem = bnbwd && prm.n_tiles == 1;          // else read through L1 from global
-  pdl_trigger();
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA);
@@ -233,8 +232,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
-  // everything above overlaps the tail of the previous kernel; from here on its results are needed
+  // everything above overlaps the tail of the previous kernel; from here on its results are needed.
+  // The trigger comes AFTER the wait: the successor may then start launching (and run its own prologue on
+  // SMs this grid has left), but never more than one kernel ahead -- triggering before the wait lets a whole
+  // chain of successors pile up on the SMs holding shared memory and TMEM columns.
   pdl_wait();
+  pdl_trigger();
   if (coef_in_smem)
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
       const int k = i / BN, cidx = i % BN;
@@ -697,7 +700,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   const bool do_bias = prm.dbias != nullptr && kt == 0 && tr == 0;
   const uint32_t bias_col = (uint32_t)(groups * N);
 
-  pdl_trigger();
   for (int i = threadIdx.x; i < WG_BOX_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
   fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
   if (threadIdx.x == 0) {
@@ -710,6 +712,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   }
   if (warp == 1) tmem_alloc_dyn(&tmem_base_slot, (uint32_t)prm.tmem_cols);
   pdl_wait();                                // the prologue above overlaps the previous kernel's tail
+  pdl_trigger();                             // after the wait: at most one successor in flight (see conv kernel)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -850,7 +853,8 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   prm.tmem_cols = alloc;
   prm.num_tiles = ceil_div(P, 64);
   const int base = prm.n_tiles * prm.k_tiles * prm.tap_ranges;
-  int splits = ceil_div(kNumSMs, base);
+  // pixel splits: fill the resident slots in ONE wave (rounding up would leave a second, nearly empty wave)
+  int splits = kNumSMs / base < 1 ? 1 : kNumSMs / base;
   if (splits > prm.num_tiles) splits = prm.num_tiles;
   prm.tiles_per_split = ceil_div(prm.num_tiles, splits);
   splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
@@ -899,7 +903,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   // with the compact layout two CTAs fit per SM: split the pixel range accordingly
   const int dyn_smem = prm.ring_bytes + WG_BOX_BYTES + 1024;
   if (two_ctas && 2 * (dyn_smem + 2048) <= 227 * 1024 && prm.tmem_cols <= 256) {
-    int splits2 = ceil_div(2 * kNumSMs, base);
+    int splits2 = 2 * kNumSMs / base < 1 ? 1 : 2 * kNumSMs / base;
     if (splits2 > prm.num_tiles) splits2 = prm.num_tiles;
     prm.tiles_per_split = ceil_div(prm.num_tiles, splits2);
     splits = ceil_div(prm.num_tiles, prm.tiles_per_split);

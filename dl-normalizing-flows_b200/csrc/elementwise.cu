@@ -20,7 +20,7 @@ bool pdl_enabled() {
   static int on = -1;
   if (on < 0) {
     const char* e = getenv("RNVP_PDL");
-    on = (e && e[0] == '1') ? 1 : 0;      // measured: no gain on this workload, so opt-in
+    on = (e && e[0] == '0') ? 0 : 1;      // on by default (+3% on the training step); RNVP_PDL=0 disables
   }
   return on != 0;
 }
@@ -58,6 +58,8 @@ __global__ void permute_kernel(int mode, const float* __restrict__ hi, const flo
                                float* __restrict__ hi_o, float* __restrict__ sq_o,
                                float* __restrict__ on_o, float* __restrict__ off_o,
                                int B, int s, int C) {
+  pdl_wait();
+  pdl_trigger();
   // one thread per element of the "factored" index space (b,i,j,k,c)
   int64_t total = (int64_t)B * s * s * 4 * C;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total;
@@ -90,8 +92,8 @@ int k_permute(PermMode mode, const float* hi, const float* sq, const float* on, 
               float* hi_o, float* sq_o, float* on_o, float* off_o, int B, int s, int C, cudaStream_t st) {
   int64_t total = (int64_t)B * s * s * 4 * C;
   if (total == 0) return RNVP_OK;
-  permute_kernel<<<grid_for(total, kThreads), kThreads, 0, st>>>((int)mode, hi, sq, on, off, hi_o, sq_o,
-                                                                  on_o, off_o, B, s, C);
+  RNVP_CUDA(launch_pdl(permute_kernel, dim3(grid_for(total, kThreads)), dim3(kThreads), 0, st, (int)mode, hi, sq, on, off, hi_o, sq_o,
+                                                                  on_o, off_o, B, s, C));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -252,6 +254,7 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* run_mean, float* run_var, float* save, int mode, int rnd, int rev) {
   pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
   float* s_shift = sm + C;
@@ -302,7 +305,6 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
       h[e] = w;
     }
   }
-  pdl_trigger();
 }
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var, float* save, int mode,
@@ -407,6 +409,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     double count, const float* __restrict__ gamma, float* dgamma,
                                     float* dbeta, float inv_world, int raw_x_sums, int rev) {
   pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -461,7 +464,6 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
       dx[e] = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
-  pdl_trigger();
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
@@ -499,8 +501,23 @@ __device__ __forceinline__ void chan_accumulate(float* sm_acc, int idx, float v)
   if ((threadIdx.x & 31) == 0) atomicAdd(&sm_acc[idx], v);
 }
 
+// The coupling kernels map one thread to one pixel and loop over channels; grid.y splits that loop so
+// that the small deep-scale tensors (4096 pixels x 48..96 channels at S = 4) still fill the machine.
+constexpr int kCplChanPerBlock = 8;
+__device__ __forceinline__ void cpl_chan_range(int cio, int& c0, int& c1) {
+  c0 = blockIdx.y * kCplChanPerBlock;
+  c1 = min(cio, c0 + kCplChanPerBlock);
+}
+static inline dim3 cpl_grid(int P, int per_block, int cio, int max_x = kNumSMs * 4) {
+  return dim3(grid_for(P, per_block, max_x), ceil_div(cio, kCplChanPerBlock));
+}
+
 __global__ void cpl_in_stats_kernel(const float* __restrict__ x, CplGeom g, double* __restrict__ sums) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float acc[2 * kMaxCio];
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
   int P = g.P();
@@ -509,19 +526,20 @@ __global__ void cpl_in_stats_kernel(const float* __restrict__ x, CplGeom g, doub
     int p = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     bool ok = p < P;
     float m = ok ? g.mask_in(p) : 0.f;
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float v = ok ? x[(int64_t)p * g.C + g.in_off + c] * m : 0.f;
       chan_accumulate(acc, c, v);
       chan_accumulate(acc, g.cio + c, v * v);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) atomicAdd(&sums[i], (double)acc[i]);
+  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x)
+    if (i % g.cio >= c0 && i % g.cio < c1) atomicAdd(&sums[i], (double)acc[i]);
 }
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   RNVP_REQUIRE(g.cio <= kMaxCio, "coupling with %d channels unsupported (max %d)", g.cio, kMaxCio);
-  cpl_in_stats_kernel<<<grid_for(g.P(), kThreads * 2, kNumSMs * 4), kThreads, 0, st>>>(x, g, sums);
+  RNVP_CUDA(launch_pdl(cpl_in_stats_kernel, cpl_grid(g.P(), kThreads * 2, g.cio), dim3(kThreads), 0, st, x, g, sums));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -531,6 +549,8 @@ __global__ void cpl_in_build_kernel(const float* __restrict__ x, CplGeom g, cons
                                     double count, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, float* run_mean, float* run_var,
                                     float* __restrict__ save, int training, float4* __restrict__ h0, int rnd) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_scale[kMaxCio], s_shift[kMaxCio];
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
     BnCoef k = training ? bn_coef_from_sums(sums[c], sums[g.cio + c], count, gamma[c], beta[c])
@@ -548,10 +568,11 @@ __global__ void cpl_in_build_kernel(const float* __restrict__ x, CplGeom g, cons
     }
   }
   __syncthreads();
-  int q4 = g.cin_pad >> 2;
-  int64_t total = (int64_t)g.P() * q4;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    int p = (int)(e / q4), q = (int)(e % q4);
+  const uint32_t q4 = (uint32_t)g.cin_pad >> 2;
+  const uint32_t total = (uint32_t)g.P() * q4;          // < 2^32: checked by the launcher (32-bit index math)
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const uint32_t pu = e / q4;
+    const int p = (int)pu, q = (int)(e - pu * q4);
     float m = g.mask_in(p);
     float r[4];
 #pragma unroll
@@ -575,8 +596,8 @@ int k_cpl_in_build(const float* x, CplGeom g, const double* sums, double count, 
                    float* h0, int tf32_round, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   int64_t total = (int64_t)g.P() * (g.cin_pad / 4);
-  cpl_in_build_kernel<<<grid_for(total, kThreads * 2), kThreads, 0, st>>>(
-      x, g, sums, count, gamma, beta, run_mean, run_var, save, training, (float4*)h0, tf32_round);
+  RNVP_REQUIRE(total < (int64_t)1 << 32, "cpl_in_build: %lld float4 elements exceed the 32-bit index range", (long long)total);
+  RNVP_CUDA(launch_pdl(cpl_in_build_kernel, dim3(grid_for(total, kThreads * 2)), dim3(kThreads), 0, st, x, g, sums, count, gamma, beta, run_mean, run_var, save, training, (float4*)h0, tf32_round));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -586,10 +607,14 @@ __global__ void cpl_fwd_a_kernel(const float* __restrict__ x, const float* __res
                                  const float* __restrict__ scale_p, const float* __restrict__ sshift_p,
                                  float* __restrict__ xprime, double* __restrict__ sums,
                                  double* __restrict__ logdet_acc, int training) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float acc[2 * kMaxCio];
   for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
   const float scale = *scale_p, sshift = *sshift_p;
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P(), hw = g.S * g.S;
   int iters = ceil_div(P, gridDim.x * blockDim.x);
   for (int it = 0; it < iters; ++it) {
@@ -597,7 +622,7 @@ __global__ void cpl_fwd_a_kernel(const float* __restrict__ x, const float* __res
     bool ok = p < P;
     float keep = ok ? 1.f - (g.ckbd ? g.mask_in(p) : 0.f) : 0.f;
     float ssum = 0.f;
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float xp = 0.f;
       if (ok) {
         float t = stt[(int64_t)p * g.cst_pad + c] * keep;
@@ -616,14 +641,14 @@ __global__ void cpl_fwd_a_kernel(const float* __restrict__ x, const float* __res
   }
   if (training) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) atomicAdd(&sums[i], (double)acc[i]);
+    for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x)
+      if (i % g.cio >= c0 && i % g.cio < c1) atomicAdd(&sums[i], (double)acc[i]);
   }
 }
 int k_cpl_fwd_a(const float* x, const float* stt, CplGeom g, const float* scale, const float* sshift,
                 float* xprime, double* sums, double* logdet_acc, int training, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_fwd_a_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      x, stt, g, scale, sshift, xprime, sums, logdet_acc, training);
+  RNVP_CUDA(launch_pdl(cpl_fwd_a_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), 0, st, x, stt, g, scale, sshift, xprime, sums, logdet_acc, training));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -635,6 +660,8 @@ __global__ void cpl_fwd_b_kernel(const float* __restrict__ xprime, const float* 
                                  int training, const float* __restrict__ scale_p,
                                  const float* __restrict__ sshift_p, float* __restrict__ y,
                                  float* __restrict__ logJ, double* __restrict__ logdet_acc) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_mean[kMaxCio], s_rstd[kMaxCio], s_hl[kMaxCio];     // hl = 0.5*log(var+eps)
   __shared__ float s_L;
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
@@ -643,7 +670,7 @@ __global__ void cpl_fwd_b_kernel(const float* __restrict__ xprime, const float* 
     s_mean[c] = k.mean;
     s_rstd[c] = k.rstd;
     s_hl[c] = 0.5f * logf(k.var + 1e-5f);
-    if (training && blockIdx.x == 0) {
+    if (training && blockIdx.x == 0 && blockIdx.y == 0) {
       save[c] = k.mean;
       save[g.cio + c] = k.rstd;
       double unb = count > 1.0 ? (double)k.var * count / (count - 1.0) : (double)k.var;
@@ -659,6 +686,8 @@ __global__ void cpl_fwd_b_kernel(const float* __restrict__ xprime, const float* 
   }
   __syncthreads();
   const float scale = logJ ? *scale_p : 0.f, sshift = logJ ? *sshift_p : 0.f;
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P(), hw = g.S * g.S;
   int iters = ceil_div(P, gridDim.x * blockDim.x);
   for (int it = 0; it < iters; ++it) {
@@ -666,7 +695,7 @@ __global__ void cpl_fwd_b_kernel(const float* __restrict__ xprime, const float* 
     bool ok = p < P;
     float keep = ok ? 1.f - (g.ckbd ? g.mask_in(p) : 0.f) : 0.f;
     if (ok) {
-      for (int c = 0; c < g.cio; ++c) {
+      for (int c = c0; c < c1; ++c) {
         float xp = xprime[(int64_t)p * g.cio + c];
         float yn = (xp - s_mean[c]) * s_rstd[c];
         y[(int64_t)p * g.C + g.on_off + c] = keep != 0.f ? yn : xp;
@@ -679,7 +708,7 @@ __global__ void cpl_fwd_b_kernel(const float* __restrict__ xprime, const float* 
         }
       }
     }
-    sample_accumulate(logdet_acc, p, P, hw, -s_L * keep);
+    if (blockIdx.y == 0) sample_accumulate(logdet_acc, p, P, hw, -s_L * keep);
   }
 }
 int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g, const double* sums,
@@ -687,8 +716,7 @@ int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g
                 const float* scale, const float* sshift, float* y, float* logJ, double* logdet_acc,
                 cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_fwd_b_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      xprime, x, stt, g, sums, count, run_mean, run_var, save, training, scale, sshift, y, logJ, logdet_acc);
+  RNVP_CUDA(launch_pdl(cpl_fwd_b_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), 0, st, xprime, x, stt, g, sums, count, run_mean, run_var, save, training, scale, sshift, y, logJ, logdet_acc));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -698,6 +726,8 @@ __global__ void cpl_inv_kernel(const float* __restrict__ y, const float* __restr
                                const float* __restrict__ run_mean, const float* __restrict__ run_var,
                                const float* __restrict__ scale_p, const float* __restrict__ sshift_p,
                                float* __restrict__ x) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_mean[kMaxCio], s_hl[kMaxCio];
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
     s_mean[c] = run_mean[c];
@@ -705,10 +735,12 @@ __global__ void cpl_inv_kernel(const float* __restrict__ y, const float* __restr
   }
   __syncthreads();
   const float scale = *scale_p, sshift = *sshift_p;
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     float keep = 1.f - (g.ckbd ? g.mask_in(p) : 0.f);
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float yv = y[(int64_t)p * g.C + g.on_off + c];
       float xt = yv * expf(s_hl[c] * keep) + s_mean[c] * keep;
       float t = stt[(int64_t)p * g.cst_pad + c] * keep;
@@ -722,8 +754,8 @@ __global__ void cpl_inv_kernel(const float* __restrict__ y, const float* __restr
 int k_cpl_inv(const float* y, const float* stt, CplGeom g, const float* run_mean, const float* run_var,
               const float* scale, const float* sshift, float* x, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_inv_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 8), kThreads, 0, st>>>(y, stt, g, run_mean, run_var,
-                                                                               scale, sshift, x);
+  RNVP_CUDA(launch_pdl(cpl_inv_kernel, cpl_grid(g.P(), kThreads, g.cio, kNumSMs * 8), dim3(kThreads), 0, st, y, stt, g, run_mean, run_var,
+                                                                                      scale, sshift, x));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -732,16 +764,20 @@ int k_cpl_inv(const float* y, const float* stt, CplGeom g, const float* run_mean
 __global__ void cpl_bwd_a_kernel(const float* __restrict__ dy, const float* __restrict__ xprime, CplGeom g,
                                  const float* __restrict__ save, const float* __restrict__ dll,
                                  double* __restrict__ sums2) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float acc[2 * kMaxCio];
   for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P();
   int iters = ceil_div(P, gridDim.x * blockDim.x);
   for (int it = 0; it < iters; ++it) {
     int p = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     bool ok = p < P;
     float keep = ok ? 1.f - (g.ckbd ? g.mask_in(p) : 0.f) : 0.f;
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float gv = 0.f, xh = 0.f;
       if (ok) {
         gv = dy[(int64_t)p * g.C + g.on_off + c] * keep;
@@ -752,8 +788,9 @@ __global__ void cpl_bwd_a_kernel(const float* __restrict__ dy, const float* __re
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) atomicAdd(&sums2[i], (double)acc[i]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x)
+    if (i % g.cio >= c0 && i % g.cio < c1) atomicAdd(&sums2[i], (double)acc[i]);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     // K = sum over pixels of dll_b * keep: keep covers half of the positions of a checkerboard
     // coupling (S*S is even whenever a mask is used) and all positions of a channelwise one
     double k = 0.0;
@@ -768,8 +805,7 @@ __global__ void cpl_bwd_a_kernel(const float* __restrict__ dy, const float* __re
 int k_cpl_bwd_a(const float* dy, const float* xprime, CplGeom g, const float* save, const float* dll,
                 double* sums2, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_bwd_a_kernel<<<grid_for(g.P(), kThreads * 2, kNumSMs * 4), kThreads, 0, st>>>(dy, xprime, g, save, dll,
-                                                                                     sums2);
+  RNVP_CUDA(launch_pdl(cpl_bwd_a_kernel, cpl_grid(g.P(), kThreads * 2, g.cio), dim3(kThreads), 0, st, dy, xprime, g, save, dll, sums2));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -782,6 +818,8 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
                                  const float* __restrict__ scale_p, const float* __restrict__ sshift_p,
                                  float* __restrict__ dst, float* __restrict__ dxdir, float* dscale,
                                  float* dsshift, int rnd) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_m1[kMaxCio], s_m2[kMaxCio];
   __shared__ float s_red[2];
   float kn = (float)(sums2[2 * g.cio] / count);
@@ -792,13 +830,15 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
   if (threadIdx.x < 2) s_red[threadIdx.x] = 0.f;
   __syncthreads();
   const float scale = *scale_p, sshift = *sshift_p;
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P(), hw = g.S * g.S;
   float a_scale = 0.f, a_shift = 0.f;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     float keep = 1.f - (g.ckbd ? g.mask_in(p) : 0.f);
     float dl_b = dll[p / hw];
     float* drow = dst + (int64_t)p * g.cst_pad;
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float mean = save[c], rstd = save[g.cio + c];
       float dyv = dy[(int64_t)p * g.C + g.on_off + c];
       float xp = xprime[(int64_t)p * g.cio + c];
@@ -817,7 +857,8 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
       a_scale += ds * th;
       a_shift += ds;
     }
-    for (int c = 2 * g.cio; c < g.cst_pad; ++c) drow[c] = 0.f;
+    if (blockIdx.y == 0)
+      for (int c = 2 * g.cio; c < g.cst_pad; ++c) drow[c] = 0.f;
   }
   a_scale = warp_sum(a_scale);
   a_shift = warp_sum(a_shift);
@@ -836,8 +877,7 @@ int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const floa
                 const float* sshift, float* dst, float* dxdir, float* dscale, float* dsshift, int tf32_round,
                 cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_bwd_b_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift, tf32_round);
+  RNVP_CUDA(launch_pdl(cpl_bwd_b_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), 0, st, dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift, tf32_round));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -845,16 +885,20 @@ int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const floa
 // in-branch backward, pass A: du = dh0[c]*1[u>0] - dh0[cio+c]*1[u<0]; sums3 = (sum du, sum du*un)
 __global__ void cpl_in_bwd_a_kernel(const float* __restrict__ dh0, const float* __restrict__ x, CplGeom g,
                                     const float* __restrict__ save, double* __restrict__ sums3) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float acc[2 * kMaxCio];
   for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) acc[i] = 0.f;
   __syncthreads();
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P();
   int iters = ceil_div(P, gridDim.x * blockDim.x);
   for (int it = 0; it < iters; ++it) {
     int p = (it * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     bool ok = p < P;
     float m = ok ? g.mask_in(p) : 0.f;
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float du = 0.f, un = 0.f;
       if (ok) {
         float v = x[(int64_t)p * g.C + g.in_off + c] * m;
@@ -868,12 +912,13 @@ __global__ void cpl_in_bwd_a_kernel(const float* __restrict__ dh0, const float* 
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x) atomicAdd(&sums3[i], (double)acc[i]);
+  for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x)
+    if (i % g.cio >= c0 && i % g.cio < c1) atomicAdd(&sums3[i], (double)acc[i]);
 }
 int k_cpl_in_bwd_a(const float* dh0, const float* x, CplGeom g, const float* save, double* sums3,
                    cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_in_bwd_a_kernel<<<grid_for(g.P(), kThreads * 2, kNumSMs * 4), kThreads, 0, st>>>(dh0, x, g, save, sums3);
+  RNVP_CUDA(launch_pdl(cpl_in_bwd_a_kernel, cpl_grid(g.P(), kThreads * 2, g.cio), dim3(kThreads), 0, st, dh0, x, g, save, sums3));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -884,20 +929,24 @@ __global__ void cpl_in_bwd_b_kernel(const float* __restrict__ dh0, const float* 
                                     const double* __restrict__ sums3, double count,
                                     const float* __restrict__ gamma, float* dgamma, float* dbeta,
                                     float* __restrict__ dx, float inv_world) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_m1[kMaxCio], s_m2[kMaxCio];
   for (int c = threadIdx.x; c < g.cio; c += blockDim.x) {
     s_m1[c] = (float)(sums3[c] / count);
     s_m2[c] = (float)(sums3[g.cio + c] / count);
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
       dbeta[c] += (float)sums3[c] * inv_world;
       dgamma[c] += (float)sums3[g.cio + c] * inv_world;
     }
   }
   __syncthreads();
+  int c0, c1;
+  cpl_chan_range(g.cio, c0, c1);
   int P = g.P();
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
     float m = g.mask_in(p);
-    for (int c = 0; c < g.cio; ++c) {
+    for (int c = c0; c < c1; ++c) {
       float v = x[(int64_t)p * g.C + g.in_off + c] * m;
       float u = fmaf(v, save[2 * g.cio + c], save[3 * g.cio + c]);
       float un = (v - save[c]) * save[g.cio + c];
@@ -917,8 +966,7 @@ int k_cpl_in_bwd_b(const float* dh0, const float* x, const float* dxdir, const f
                    const float* save, const double* sums3, double count, const float* gamma, float* dgamma,
                    float* dbeta, float* dx, float inv_world, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  cpl_in_bwd_b_kernel<<<grid_for(g.P(), kThreads, kNumSMs * 4), kThreads, 0, st>>>(
-      dh0, x, dxdir, dy, g, save, sums3, count, gamma, dgamma, dbeta, dx, inv_world);
+  RNVP_CUDA(launch_pdl(cpl_in_bwd_b_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), 0, st, dh0, x, dxdir, dy, g, save, sums3, count, gamma, dgamma, dbeta, dx, inv_world));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -1063,6 +1111,8 @@ int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbas
 }
 // dg = sum dw * v/||v|| ; dv = (g/||v||) * (dw - dg * v/||v||)
 __global__ void weightnorm_bwd_kernel(const WnJob* __restrict__ jobs, const float* __restrict__ dwbase) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sm[8];
   const WnJob j = jobs[blockIdx.y];
   int co = blockIdx.x;
@@ -1095,7 +1145,7 @@ int k_weightnorm_bwd(const WnJob* jobs_dev, int njobs, int max_cout, const float
                      cudaStream_t st) {
   (void)wbase;
   if (njobs == 0) return RNVP_OK;
-  weightnorm_bwd_kernel<<<dim3(max_cout, njobs), 128, 0, st>>>(jobs_dev, dwbase);
+  RNVP_CUDA(launch_pdl(weightnorm_bwd_kernel, dim3(max_cout, njobs), dim3(128), 0, st, jobs_dev, dwbase));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

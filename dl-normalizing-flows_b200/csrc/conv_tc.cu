@@ -638,12 +638,13 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
 // One CTA owns (k-tile, n-tile, tap range, pixel range): per pixel tile it loads the dy boxes once,
 // then one 4-box A stage per M-group, issues 8 x (K = 8 pixels) MMAs per group into that group's
 // TMEM columns, and finally flushes the accumulators with coalesced fp32 atomics.  The bias gradient
-// is one more M-group whose A operand is a constant all-ones tile.
+// (column sums of dy) is taken from the staged dy boxes in shared memory by the epilogue warps, which
+// are otherwise idle during the main loop -- it costs no tensor-core work and no extra traffic.
 // ---------------------------------------------------------------------------------------------
 constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
 constexpr int WG_MAX_STAGES = 16;              // ring depths are chosen per launch from the actual stage sizes
 constexpr int WG_RING_BYTES = 192 * 1024;     // A ring + B ring
-constexpr int WG_SMEM = WG_RING_BYTES + WG_BOX_BYTES + 1024;
+constexpr int WG_SMEM = WG_RING_BYTES + 1024;
 constexpr int WG_MAX_GROUPS = 16;
 
 struct WgradTcParams {
@@ -656,7 +657,7 @@ struct WgradTcParams {
   int tiles_per_split, num_tiles;           // 64-pixel tiles
   int tmem_cols;
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
-  int ring_bytes;                           // A ring + MMA slack + B ring; the all-ones box follows
+  int ring_bytes;                           // A ring + MMA slack + B ring
   int a_lbo;                                // byte stride between the 32-row groups of the A operand
 };
 
@@ -677,7 +678,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   const int WG_A_STAGE_BYTES = prm.a_stage_bytes, WG_B_STAGE_BYTES = prm.b_stage_bytes;
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + prm.ring_bytes - WG_B_STAGES * WG_B_STAGE_BYTES;
-  float* ones = reinterpret_cast<float*>(smem + prm.ring_bytes);
   __shared__ __align__(8) uint64_t a_full[WG_MAX_STAGES], a_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t b_full[WG_MAX_STAGES], b_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -698,15 +698,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   const int t_begin = blockIdx.y * prm.tiles_per_split;
   const int t_end = min(prm.num_tiles, t_begin + prm.tiles_per_split);
   const bool do_bias = prm.dbias != nullptr && kt == 0 && tr == 0;
-  const uint32_t bias_col = (uint32_t)(groups * N);
 
-  for (int i = threadIdx.x; i < WG_BOX_BYTES / 4; i += blockDim.x) ones[i] = 1.0f;
-  fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmDy);
     prefetch_tmap(&tmX);
     for (int s = 0; s < WG_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    // a dy stage is released by the MMA commit and, when this CTA owns the bias gradient, by the four
+    // epilogue warps that read the boxes for the column sums
+    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], do_bias ? 5 : 1); }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
   }
@@ -752,7 +751,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       // ===================== MMA issuer =====================
       if (lane == 0) {
         const uint32_t idesc = make_idesc_tf32(128, N, 1, 1);
-        const uint32_t ones_addr = smem_u32(ones);
         int ai = 0;
         for (int t = t_begin; t < t_end; ++t) {
           const int bi = t - t_begin, bs = bi % WG_B_STAGES;
@@ -760,12 +758,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
           tc_fence_after();
           const uint32_t b_addr = smem_u32(b_ring + bs * WG_B_STAGE_BYTES);
           const uint32_t acc = (t != t_begin);
-          if (do_bias) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)       // A = ones (LBO 0: all four 32-row groups alias one box)
-              umma_tf32(tmem_base + bias_col, make_desc(ones_addr + ks * 1024, 0, 512, kLayoutSw128Base32),
-                        make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
-          }
           for (int mg = 0; mg < groups; ++mg, ++ai) {
             const int as = ai % WG_A_STAGES;
             mbar_wait(&a_full[as], (ai / WG_A_STAGES) & 1);
@@ -787,6 +779,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       const int m = q * 32 + lane;               // accumulator row = (tap_local, k)
       const int kc = kb * 32;
       const int tl = m / kc, k = m % kc;
+      if (do_bias) {
+        // dbias[n] = sum_p dy[p,n]: warp q owns dy box q (32 channels x 64 pixel rows of 128 bytes).  Within a
+        // row the four 32-byte chunks are XOR-permuted by (row & 3) ("128B swizzle, 32B atom" = Swizzle<2,5,2>),
+        // so lane w accumulates word w separately per row phase and un-permutes at the end.
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int t = t_begin; t < t_end; ++t) {
+          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
+          mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+          if (q < nbx) {
+            const float* box = reinterpret_cast<const float*>(b_ring + bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES);
+#pragma unroll 16
+            for (int r = 0; r < 64; ++r) part[r & 3] += box[r * 32 + lane];
+          }
+          __syncwarp();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_empty[bs])) : "memory");
+        }
+        if (q < nbx) {
+#pragma unroll
+          for (int ph = 0; ph < 4; ++ph) {
+            const int ch = n0 + q * 32 + ((((lane >> 3) ^ ph) << 3) | (lane & 7));
+            if (ch < prm.n) atomicAdd(prm.dbias + ch, part[ph]);
+          }
+        }
+      }
       mbar_wait(&acc_bar, 0);
       tc_fence_after();
       for (int mg = 0; mg < groups; ++mg) {
@@ -800,17 +816,6 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + c0 + j < prm.n) atomicAdd(dst + (int64_t)(c0 + j) * prm.kpad, v[j]);
-          }
-        }
-      }
-      if (do_bias) {
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          float v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + bias_col + c0, v);
-          if (m == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < prm.n) atomicAdd(prm.dbias + n0 + c0 + j, v[j]);
           }
         }
       }
@@ -841,14 +846,14 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   prm.tpm = prm.kb == 3 ? 1 : 4 / prm.kb;
   if (prm.tpm > a.taps) prm.tpm = a.taps;
   const int N = pad_to(a.n < 128 ? a.n : 128, 32);
-  int max_groups = 512 / N - 1;                   // one N-wide column block is kept for the bias group
+  int max_groups = 512 / N;
   if (max_groups > WG_MAX_GROUPS) max_groups = WG_MAX_GROUPS;
   int groups_total = ceil_div(a.taps, prm.tpm);
   prm.tap_ranges = ceil_div(groups_total, max_groups);
   int groups_per_range = ceil_div(groups_total, prm.tap_ranges);
   prm.taps_per_range = groups_per_range * prm.tpm;
   prm.tap_ranges = ceil_div(a.taps, prm.taps_per_range);
-  int cols = (groups_per_range + 1) * N, alloc = 32;
+  int cols = groups_per_range * N, alloc = 32;
   while (alloc < cols) alloc <<= 1;
   prm.tmem_cols = alloc;
   prm.num_tiles = ceil_div(P, 64);
@@ -901,7 +906,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
     attr_set = true;
   }
   // with the compact layout two CTAs fit per SM: split the pixel range accordingly
-  const int dyn_smem = prm.ring_bytes + WG_BOX_BYTES + 1024;
+  const int dyn_smem = prm.ring_bytes + 1024;
   if (two_ctas && 2 * (dyn_smem + 2048) <= 227 * 1024 && prm.tmem_cols <= 256) {
     int splits2 = 2 * kNumSMs / base < 1 ? 1 : 2 * kNumSMs / base;
     if (splits2 > prm.num_tiles) splits2 = prm.num_tiles;

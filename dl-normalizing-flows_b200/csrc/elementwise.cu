@@ -404,7 +404,7 @@ int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C,
 }
 
 __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__ x,
-                                    float4* dx, int accumulate, int64_t n4, int C, int ld,
+                                    float4* dx, const float4* add, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
                                     float* dbeta, float inv_world, int raw_x_sums, int rev) {
@@ -442,7 +442,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
         if (rev) e = n4 - 1 - e;
         gv[u] = gm[e];
         xv[u] = __ldcs(&x[e]);                 // last use of the saved activation
-        if (accumulate) ov[u] = dx[e];
+        if (add) ov[u] = add[e];
       }
     }
 #pragma unroll
@@ -458,20 +458,20 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
         float xh = (xx[k] - s_mean[c + k]) * s_rstd[c + k];
         r[k] = s_a[c + k] * (gg[k] - s_m1[c + k] - xh * s_m2[c + k]);
       }
-      if (accumulate) {
+      if (add) {
         r[0] += ov[u].x; r[1] += ov[u].y; r[2] += ov[u].z; r[3] += ov[u].w;
       }
       dx[e] = make_float4(r[0], r[1], r[2], r[3]);
     }
   }
 }
-int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
+int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
                    float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
-                       5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, accumulate, n4, C, ld,
+                       5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, (const float4*)add, n4, C, ld,
                        save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, next_sweep_dir()));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;

@@ -40,9 +40,9 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
 // gm = g * 1[h>0] written to gm_out; sums2[0:C] += sum gm, sums2[C:2C] += sum gm*xhat
 int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C, int ld,
                     const float* save, double* sums2, cudaStream_t st);
-// dx (= or +=) gamma*rstd*(gm - m1 - xhat*m2); block 0 adds dgamma/dbeta.  raw_x_sums: sums2[C:2C] holds
-// sum gm*x (fused dgrad epilogue) instead of sum gm*xhat
-int k_bn_bwd_apply(const float* gm, const float* x, float* dx, int accumulate, int P, int C, int ld,
+// dx = gamma*rstd*(gm - m1 - xhat*m2) (+ add, which may alias dx); block 0 adds dgamma/dbeta.
+// raw_x_sums: sums2[C:2C] holds sum gm*x (fused dgrad epilogue) instead of sum gm*xhat
+int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
                    float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st);
 

@@ -100,6 +100,9 @@ struct Layout {
   std::vector<size_t> cpl_act;       // byte offset of each coupling's activation block
   // flow-level buffers (float counts)
   size_t img;                        // B*C*H*W
+  // backward scratch (float counts): `sets` sets of `nbuf` trunk-sized buffers followed by the aux block
+  size_t maxPD, maxaux, set_floats;
+  int nbuf, sets;
 };
 
 }  // namespace
@@ -122,6 +125,14 @@ struct rnvp_plan {
   // data parallel
   DpState dp;
   int& world = dp.world;
+  // wgrad side stream (mode 2): weight gradients are off the critical path of the backward pass, so they
+  // run on a second, lower-priority stream and fill the SMs / HBM time the dgrad chain leaves idle
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ring[32] = {};
+  unsigned ev_next = 0;
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};   // side stream finished the coupling that used scratch set 0 / 1
+  bool done_valid[2] = {false, false};
+  cudaEvent_t ev_join = nullptr;
   // forward bookkeeping for backward
   int saved_batch = -1;
   int saved_mode = 1;
@@ -332,8 +343,14 @@ Layout compute_layout(const rnvp_plan* p, int B, int mode) {
   if (mode < 1) act_total = align_up(maxact, 256);
   L.act = take(act_total * 4);
   for (auto& v : L.cpl_act) v += L.act;
-  // scratch: H + (mode 1: T0, T1, DA, DO + dst/dxdir/dh0)
-  L.scratch = take((mode >= 1 ? 5 * maxPD + maxaux : maxPD) * 4);
+  // scratch.  inference: H.  mode 1: H, T0, T1, DA, DO + aux (dst/dxdir/dh0), buffers reused layer to layer.
+  // mode 2: every gradient tensor of a coupling's s/t net gets its own buffer (5 per residual block + 2), in
+  // two sets used by alternate couplings, so that the side-stream wgrads never race with the dgrad chain.
+  L.maxPD = maxPD; L.maxaux = maxaux;
+  L.nbuf = mode == 2 ? 5 * p->cfg.res_blocks + 2 : (mode == 1 ? 5 : 1);
+  L.sets = mode == 2 ? 2 : 1;
+  L.set_floats = (size_t)L.nbuf * maxPD + (mode >= 1 ? maxaux : 0);
+  L.scratch = take(L.sets * L.set_floats * 4);
   L.total = o;
   return L;
 }
@@ -347,6 +364,8 @@ struct Ctx {
   char* ws;
   int B, mode;
   cudaStream_t st;
+  cudaStream_t wst;                  // stream of the wgrad kernels (== st unless the side stream is active)
+  bool side_on;
   float* weights() const { return reinterpret_cast<float*>(ws + L.weights); }
   float* dw() const { return reinterpret_cast<float*>(ws + L.dw); }
   double* ws_acc() const { return reinterpret_cast<double*>(ws + L.accum); }
@@ -357,12 +376,27 @@ struct Ctx {
   float* save(size_t off) const { return reinterpret_cast<float*>(ws + L.saves) + off; }
   float* act(int ci, size_t off) const { return reinterpret_cast<float*>(ws + L.cpl_act[ci]) + off; }
   float* scratch() const { return reinterpret_cast<float*>(ws + L.scratch); }
+  // backward scratch of coupling ci: trunk-sized buffer k, and the aux block behind the buffers
+  float* set_base(int ci) const { return scratch() + (size_t)(L.sets == 2 ? (ci & 1) : 0) * L.set_floats; }
+  float* buf(int ci, int k) const { return set_base(ci) + (size_t)k * L.maxPD; }
+  float* aux(int ci) const { return set_base(ci) + (size_t)L.nbuf * L.maxPD; }
 };
+
+bool side_stream_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_WGRAD_STREAM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
 
 int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* stream, Ctx* c) {
   RNVP_REQUIRE(p && p->bound, "plan is not bound to parameters (call rnvp_plan_bind)");
   RNVP_REQUIRE(B > 0, "batch must be positive");
   c->p = p; c->B = B; c->mode = mode; c->st = (cudaStream_t)stream;
+  c->side_on = mode == 2 && p->side != nullptr && side_stream_enabled();
+  c->wst = c->side_on ? p->side : c->st;
   c->L = compute_layout(p, B, mode);
   if (ws == nullptr || ws_bytes < c->L.total) {
     set_error("workspace too small: need %zu bytes, got %zu", c->L.total, ws_bytes);
@@ -406,12 +440,32 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
   a.taps = cv.taps; a.ldy = ldy;
   return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
 }
+// the side stream waits for everything enqueued on the main stream so far
+int fork_to_side(const Ctx& c) {
+  if (!c.side_on) return RNVP_OK;
+  rnvp_plan* p = c.p;
+  cudaEvent_t e = p->ev_ring[p->ev_next++ % 32];
+  RNVP_CUDA(cudaEventRecord(e, c.st));
+  RNVP_CUDA(cudaStreamWaitEvent(c.wst, e, 0));
+  return RNVP_OK;
+}
+// the main stream waits for everything enqueued on the side stream; forgets the per-set markers
+int join_side(const Ctx& c) {
+  if (!c.side_on) return RNVP_OK;
+  rnvp_plan* p = c.p;
+  RNVP_CUDA(cudaEventRecord(p->ev_join, c.wst));
+  RNVP_CUDA(cudaStreamWaitEvent(c.st, p->ev_join, 0));
+  p->done_valid[0] = p->done_valid[1] = false;
+  return RNVP_OK;
+}
+
 int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy, int lddy, int S, float* dbias) {
-  ProfScope ps(PROF_WGRAD, S, cv.taps, cv.cin, cv.cout, c.st);
+  RNVP_TRY(fork_to_side(c));                 // dy (and a recomputed x) were produced on the main stream
+  ProfScope ps(PROF_WGRAD, S, cv.taps, cv.cin, cv.cout, c.wst);
   WgradArgs a{};
   a.x = x; a.dy = dy; a.dw = c.dw() + cv.dw_off; a.dbias = dbias;
   a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
-  return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.st) : k_conv_wgrad_fp32(a, c.st);
+  return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.wst) : k_conv_wgrad_fp32(a, c.wst);
 }
 
 // ------------------------------------------------------------------------------------

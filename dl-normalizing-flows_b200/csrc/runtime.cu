@@ -344,10 +344,10 @@ Layout compute_layout(const rnvp_plan* p, int B, int mode) {
   L.act = take(act_total * 4);
   for (auto& v : L.cpl_act) v += L.act;
   // scratch.  inference: H.  mode 1: H, T0, T1, DA, DO + aux (dst/dxdir/dh0), buffers reused layer to layer.
-  // mode 2: every gradient tensor of a coupling's s/t net gets its own buffer (5 per residual block + 2), in
+  // mode 2: every gradient tensor of a coupling's s/t net gets its own buffer (5 per residual block + 3), in
   // two sets used by alternate couplings, so that the side-stream wgrads never race with the dgrad chain.
   L.maxPD = maxPD; L.maxaux = maxaux;
-  L.nbuf = mode == 2 ? 5 * p->cfg.res_blocks + 2 : (mode == 1 ? 5 : 1);
+  L.nbuf = mode == 2 ? 5 * p->cfg.res_blocks + 3 : (mode == 1 ? 5 : 1);
   L.sets = mode == 2 ? 2 : 1;
   L.set_floats = (size_t)L.nbuf * maxPD + (mode >= 1 ? maxaux : 0);
   L.scratch = take(L.sets * L.set_floats * 4);
@@ -513,23 +513,22 @@ int net_forward(const Ctx& c, int ci, int training) {
   return RNVP_OK;
 }
 
-// backward of the s/t network: dst [P,cst_pad] -> dh0 [P,cin_pad]; weight grads into the dw scratch
+// backward of the s/t network: dst [P,cst_pad] -> dh0 [P,cin_pad]; weight grads into the dw scratch.
+// Gradient buffers come from c.buf(ci, k).  Mode 1 has five of them and reuses them layer to layer
+// (H = recomputed activation, T0, T1, DA, DO); mode 2 takes a fresh buffer for every gradient tensor so
+// that the wgrad kernels, which run on the side stream, can read their dy operand at any later time.
 int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   rnvp_plan* p = c.p;
   const CouplingDesc& d = p->cpl[ci];
   const int R = p->cfg.res_blocks, S = d.S, ld = d.ldD, Pn = c.B * S * S;
   const double count = (double)Pn * p->world;
   CplAct A = cpl_act(p, d, c.B, c.mode);
-  size_t PD = align_up((size_t)Pn * ld, 64);
-  size_t maxPD = 0;
-  for (auto& q : p->cpl) maxPD = std::max(maxPD, align_up((size_t)c.B * q.S * q.S * q.ldD, 64));
-  (void)PD;
-  float* Hs = c.scratch();
+  const bool fresh = c.mode == 2;
+  int next = 0;
+  // mode 1 roles: 0 = H, 1 = T0, 2 = T1, 3 = DA, 4 = DO
+  auto take = [&](int role) { return fresh ? c.buf(ci, next++) : c.buf(ci, role); };
+  float* Hs = fresh ? nullptr : c.buf(ci, 0);
   float* H = Hs;
-  float* T0 = Hs + maxPD;
-  float* T1 = T0 + maxPD;
-  float* DA = T1 + maxPD;
-  float* DO = DA + maxPD;
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
   auto recompute = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
@@ -542,12 +541,11 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     return k_bn_relu(x, H, Pn, b.C, ld, nullptr, count, nullptr, nullptr, nullptr, nullptr, c.save(b.save), 2,
                      p->math == RNVP_MATH_TF32, c.st);
   };
-  // BN+ReLU backward in place on g: g <- d(pre-BN input); out==nullptr: in place, else (+=) into out
   // dgrad of `cv` applied to `dy`, then ReLU+BN backward through BN `bi` whose raw input was `x`:
-  // g <- d(pre-BN input) (in place, or (+=) into out).  With the tensor-core tier the mask and the two
+  // g <- masked gradient, out = d(pre-BN input) (+ add).  With the tensor-core tier the mask and the two
   // reductions ride in the dgrad epilogue; otherwise a separate reduce kernel does them.
   auto dgrad_bn_bwd = [&](const ConvDesc& cvd, const float* dy, int bi, float* g, const float* x, float* out,
-                          int accumulate) -> int {
+                          const float* add) -> int {
     const BnDesc& b = d.bns[bi];
     ConvArgs a = conv_args(c, cvd, true, dy, S, g, ld, nullptr, nullptr, nullptr);
     const bool fused = p->math == RNVP_MATH_TF32 && conv_tf32_fusable(a);
@@ -561,41 +559,54 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     ProfScope ps(PROF_BN_BWD, S, 0, b.C, b.C, c.st);
     if (!fused) RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
     RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
-    return k_bn_bwd_apply(g, x, out ? out : g, accumulate, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
+    return k_bn_bwd_apply(g, x, out, add, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
                           P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b),
                           1.0f / p->world, fused ? 1 : 0, c.st);
   };
   const ConvDesc* cv = d.convs.data();
   const ConvDesc& oc = cv[2 + 4 * R];
-  // out_block: st = conv(relu(bn(skip)))
-  RNVP_TRY(recompute(3 * R, c.act(ci, A.skip)));
-  RNVP_TRY(run_wgrad(c, oc, H, dst, d.cst_pad, S, gbias(oc)));
-  RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, T0, c.act(ci, A.skip), DO, 0));
+  // out_block: st = conv(relu(bn(skip)));  DO = d(skip sum), constant for the rest of the coupling
+  float* DO = take(4);
+  {
+    float* G0 = take(1);
+    RNVP_TRY(recompute(3 * R, c.act(ci, A.skip)));
+    RNVP_TRY(run_wgrad(c, oc, H, dst, d.cst_pad, S, gbias(oc)));
+    RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, G0, c.act(ci, A.skip), DO, nullptr));
+  }
+  const float* DA = nullptr;               // d(a_{i+1}) accumulated so far
   for (int i = R - 1; i >= 0; --i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
     float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
     float *u1 = c.act(ci, A.u1[i]), *u2 = c.act(ci, A.u2[i]);
     // skip += core_skip_i(a_{i+1})
+    float* DAc = take(3);
     RNVP_TRY(run_wgrad(c, *cs, an, DO, ld, S, gbias(*cs)));
-    RNVP_TRY(run_conv(c, *cs, true, DO, S, DA, ld, nullptr, i == R - 1 ? nullptr : DA, nullptr));
+    RNVP_TRY(run_conv(c, *cs, true, DO, S, DAc, ld, nullptr, DA, nullptr));
     // a_{i+1} = a_i + rb6(relu(bn3(u2)))
+    float* G3 = take(1);
     RNVP_TRY(recompute(3 * i + 2, u2));
-    RNVP_TRY(run_wgrad(c, *rb6, H, DA, ld, S, gbias(*rb6)));
-    RNVP_TRY(dgrad_bn_bwd(*rb6, DA, 3 * i + 2, T0, u2, nullptr, 0));
+    RNVP_TRY(run_wgrad(c, *rb6, H, DAc, ld, S, gbias(*rb6)));
+    RNVP_TRY(dgrad_bn_bwd(*rb6, DAc, 3 * i + 2, G3, u2, G3, nullptr));
     // u2 = rb3(relu(bn2(u1)))
+    float* G2 = take(2);
     RNVP_TRY(recompute(3 * i + 1, u1));
-    RNVP_TRY(run_wgrad(c, *rb3, H, T0, ld, S, nullptr));
-    RNVP_TRY(dgrad_bn_bwd(*rb3, T0, 3 * i + 1, T1, u1, nullptr, 0));
+    RNVP_TRY(run_wgrad(c, *rb3, H, G3, ld, S, nullptr));
+    RNVP_TRY(dgrad_bn_bwd(*rb3, G3, 3 * i + 1, G2, u1, G2, nullptr));
     // u1 = rb0(relu(bn1(a_i)))
+    float* G1 = take(1);
+    float* DAn = take(3);
     RNVP_TRY(recompute(3 * i, ai));
-    RNVP_TRY(run_wgrad(c, *rb0, H, T1, ld, S, nullptr));
-    RNVP_TRY(dgrad_bn_bwd(*rb0, T1, 3 * i, T0, ai, DA, 1));
+    RNVP_TRY(run_wgrad(c, *rb0, H, G2, ld, S, nullptr));
+    RNVP_TRY(dgrad_bn_bwd(*rb0, G2, 3 * i, G1, ai, DAn, DAc));
+    DA = DAn;
   }
   // skip = in_skip(a0) (+...); a0 = in_block(h0)
+  float* DAf = take(3);
   RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));
-  RNVP_TRY(run_conv(c, cv[1], true, DO, S, DA, ld, nullptr, DA, nullptr));
-  RNVP_TRY(run_wgrad(c, cv[0], c.act(ci, A.h0), DA, ld, S, gbias(cv[0])));
-  RNVP_TRY(run_conv(c, cv[0], true, DA, S, dh0, d.cin_pad, nullptr, nullptr, nullptr));
+  RNVP_TRY(run_conv(c, cv[1], true, DO, S, DAf, ld, nullptr, DA, nullptr));
+  RNVP_TRY(run_wgrad(c, cv[0], c.act(ci, A.h0), DAf, ld, S, gbias(cv[0])));
+  RNVP_TRY(run_conv(c, cv[0], true, DAf, S, dh0, d.cin_pad, nullptr, nullptr, nullptr));
+  if (fresh) RNVP_REQUIRE(next <= c.L.nbuf, "internal: backward scratch overrun (%d > %d)", next, c.L.nbuf);
   return RNVP_OK;
 }
 
@@ -657,14 +668,15 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
   const double count = (double)g.P() * p->world;
   const float* x = p->x_in[ci];
   RNVP_REQUIRE(x != nullptr, "coupling %s: backward without a training forward", d.name.c_str());
-  size_t maxPD = 0;
-  for (auto& q : p->cpl) maxPD = std::max(maxPD, align_up((size_t)c.B * q.S * q.S * q.ldD, 64));
-  float* aux = c.scratch() + 5 * maxPD;
+  float* aux = c.aux(ci);
   size_t Pn = g.P();
   float* dst = aux;
   float* dxdir = dst + align_up(Pn * d.cst_pad, 64);
   float* dh0 = dxdir + align_up(Pn * d.cio, 64);
-  RNVP_CUDA(cudaMemsetAsync(c.dw(), 0, d.dw_floats * 4, c.st));
+  const int set = c.L.sets == 2 ? (ci & 1) : 0;
+  // the coupling that used this scratch set before must have finished on the side stream
+  if (c.side_on && p->done_valid[set]) RNVP_CUDA(cudaStreamWaitEvent(c.st, p->ev_done[set], 0));
+  RNVP_CUDA(cudaMemsetAsync(c.dw(), 0, d.dw_floats * 4, c.wst));
   RNVP_TRY(k_cpl_bwd_a(dy, c.act(ci, A.xprime), g, c.save(d.save_out), dll, c.sb(d.sb_cpl), c.st));
   RNVP_TRY(sync_stats(c, c.sb(d.sb_cpl), 2 * d.cio + 1));
   RNVP_TRY(k_cpl_bwd_b(dy, c.act(ci, A.xprime), x, c.act(ci, A.st), g, c.save(d.save_out), c.sb(d.sb_cpl), count,
@@ -676,7 +688,12 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
   RNVP_TRY(k_cpl_in_bwd_b(dh0, x, dxdir, dy, g, c.save(d.save_in), c.sb(d.sb_in), count,
                           P_<float>(p, d, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_W), G_(p, ci, SLOT_INBN_B), dx,
                           1.0f / p->world, c.st));
-  RNVP_TRY(k_weightnorm_bwd(p->d_jobs + d.job0, (int)d.convs.size(), p->max_cout, c.weights(), c.dw(), c.st));
+  // weight-norm backward follows the wgrads of this coupling on their stream
+  RNVP_TRY(k_weightnorm_bwd(p->d_jobs + d.job0, (int)d.convs.size(), p->max_cout, c.weights(), c.dw(), c.wst));
+  if (c.side_on) {
+    RNVP_CUDA(cudaEventRecord(p->ev_done[set], c.wst));
+    p->done_valid[set] = true;
+  }
   return RNVP_OK;
 }
 
@@ -791,6 +808,13 @@ int rnvp_plan_destroy(rnvp_plan* p) {
   if (!p) return RNVP_OK;
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_segs) cudaFree(p->d_segs);
+  if (p->side) {
+    cudaStreamSynchronize(p->side);
+    cudaStreamDestroy(p->side);
+    for (auto& e : p->ev_ring) cudaEventDestroy(e);
+    for (auto& e : p->ev_done) cudaEventDestroy(e);
+    cudaEventDestroy(p->ev_join);
+  }
   delete p;
   return RNVP_OK;
 }
@@ -853,6 +877,14 @@ int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* 
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (!p->side) {
+    int lo = 0, hi = 0;                         // lowest priority: the dgrad chain on the caller's stream goes first
+    RNVP_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RNVP_CUDA(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, lo));
+    for (auto& e : p->ev_ring) RNVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : p->ev_done) RNVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    RNVP_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  }
   if (!p->d_jobs) RNVP_CUDA(cudaMalloc(&p->d_jobs, jobs.size() * sizeof(WnJob)));
   if (!p->d_segs) RNVP_CUDA(cudaMalloc(&p->d_segs, segs.size() * sizeof(Seg)));
   RNVP_CUDA(cudaMemcpyAsync(p->d_jobs, jobs.data(), jobs.size() * sizeof(WnJob), cudaMemcpyHostToDevice, st));
@@ -1001,7 +1033,10 @@ int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scal
     for (int i = 0; i < n; ++i, --ci) {
       float* dx = f.G[k ^= 1];
       RNVP_TRY(coupling_backward(c, ci, dcur, dll, dx));
-      if (p->world > 1) RNVP_TRY(dp_coupling_done(&p->dp, ci, c.st));   // overlap: reduce finished buckets
+      if (p->world > 1) {                      // overlap: reduce finished buckets
+        RNVP_TRY(fork_to_side(c));             // the bucket needs both streams' gradients of this coupling
+        RNVP_TRY(dp_coupling_done(&p->dp, ci, c.wst));
+      }
       dcur = dx;
     }
     return RNVP_OK;
@@ -1023,6 +1058,7 @@ int rnvp_flow_backward(rnvp_plan* p, const float* dll, const float* dweight_scal
     RNVP_TRY(run_group(3));
   }
   if (dx_nchw) RNVP_TRY(k_nhwc_to_nchw(dcur, dx_nchw, batch, cf.channels, cf.image_size, cf.image_size, c.st));
+  RNVP_TRY(join_side(c));
   if (p->world > 1) RNVP_TRY(dp_join(&p->dp, c.st));
   p->saved_batch = -1;
   return RNVP_OK;
@@ -1132,6 +1168,7 @@ int rnvp_coupling_backward(rnvp_plan* p, int ci, const float* dy_nchw, const flo
   RNVP_TRY(k_nchw_to_nhwc(dy_nchw, f.G[0], batch, d.C, d.S, d.S, c.st));
   RNVP_TRY(k_gather_first(dlogJ_nchw, f.dll, batch, d.C * d.S * d.S, c.st));
   RNVP_TRY(coupling_backward(c, ci, f.G[0], f.dll, f.G[1]));
+  RNVP_TRY(join_side(c));
   RNVP_TRY(k_nhwc_to_nchw(f.G[1], dx_nchw, batch, d.C, d.S, d.S, c.st));
   p->saved_coupling = -1;
   p->saved_batch = -1;

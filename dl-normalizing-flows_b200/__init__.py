@@ -19,7 +19,8 @@ from modules_realnvp import (  # noqa: E402
     ResidualBlock, ResidualModule, WeightNormConv2d)
 from utils import Hyperparameters, logit_transform  # noqa: E402
 from rnvp_engine import set_default_math  # noqa: E402
+import rnvp_optim  # noqa: E402
 
 __all__ = ["RealNVP", "AbstractCoupling", "ChannelwiseAffineCoupling", "CheckerboardAffineCoupling",
            "ResidualBlock", "ResidualModule", "WeightNormConv2d", "Hyperparameters", "logit_transform",
-           "set_default_math", "rnvp_cabi"]
+           "set_default_math", "rnvp_cabi", "rnvp_optim"]

@@ -8,10 +8,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
        -Xcompiler -Wall -Xcompiler -Wno-unused-function --expt-relaxed-constexpr "$@")
 mkdir -p "$HERE/build"
 pids=()
-for f in elementwise conv_simt conv_tc runtime dp; do
+for f in elementwise conv_simt conv_tc runtime dp optim; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/build/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/{elementwise,conv_simt,conv_tc,runtime,dp}.o -lcudart -lcuda -ldl
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/build/{elementwise,conv_simt,conv_tc,runtime,dp,optim}.o -lcudart -lcuda -ldl
 echo "built $OUT"

@@ -395,7 +395,7 @@ int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* str
   RNVP_REQUIRE(p && p->bound, "plan is not bound to parameters (call rnvp_plan_bind)");
   RNVP_REQUIRE(B > 0, "batch must be positive");
   c->p = p; c->B = B; c->mode = mode; c->st = (cudaStream_t)stream;
-  c->side_on = mode == 2 && p->side != nullptr && side_stream_enabled();
+  c->side_on = mode == 2 && p->side != nullptr && side_stream_enabled() && !g_prof_on;
   c->wst = c->side_on ? p->side : c->st;
   c->L = compute_layout(p, B, mode);
   if (ws == nullptr || ws_bytes < c->L.total) {

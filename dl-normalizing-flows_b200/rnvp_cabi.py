@@ -71,6 +71,9 @@ def _load():
         "rnvp_dp_set_grad_layout": (i32, [vp, vp, C.POINTER(C.c_int64), C.c_int64]),
         "rnvp_dp_finalize": (i32, [vp]),
         "rnvp_dp_allreduce": (i32, [vp, vp, sz, vp]),
+        "rnvp_adam_create": (i32, [C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32, C.POINTER(vp)]),
+        "rnvp_adam_destroy": (i32, [vp]),
+        "rnvp_adam_step": (i32, [vp, vp, vp, vp, C.c_int64] + [C.c_double] * 5 + [C.c_int64, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError here = header/library mismatch

@@ -62,6 +62,7 @@ class Engine:
         self._tensors: List[Optional[torch.Tensor]] = []
         self._trainable: List[nn.Parameter] = []
         self._flat_grad: Optional[torch.Tensor] = None
+        self.grad_writes = 0                # backward passes that have added into the flat gradient (rnvp_optim)
         self._views: List[torch.Tensor] = []
         self._ws = {0: None, 1: None, 2: None}
         self.train_mode = None              # None = pick 2 (keep activations) when memory allows, else 1
@@ -238,6 +239,7 @@ class Engine:
         dev = dll.device
         B = dll.shape[0]
         self.prepare_grads()
+        self.grad_writes += 1
         dx = torch.empty_like(x_like) if want_dx else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.rnvp_flow_backward(self.handle, ptr(dll), ptr(dws), ptr(dx), B, ptr(ws), ws.numel(),
@@ -292,6 +294,7 @@ class Engine:
         dev = dy.device
         B = dy.shape[0]
         self.prepare_grads()
+        self.grad_writes += 1
         dx = torch.empty_like(dy)
         stream = torch.cuda.current_stream(dev).cuda_stream
         check(lib.rnvp_coupling_backward(self.handle, idx, ptr(dy.contiguous()), ptr(dlogj.contiguous()), ptr(dx), B,

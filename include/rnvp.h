@@ -69,7 +69,8 @@ unsigned long long rnvp_launch_count(void);
 /* Measurement hooks: with profiling on, every conv / dgrad / wgrad / batch-norm launch is bracketed by
  * CUDA events on its own stream.  rnvp_prof_collect synchronises, sums the intervals per kernel class
  * into rows of 7 doubles (kind 0 conv 1 dgrad 2 wgrad 3 bn 4 bn-bwd, S, taps, cin, cout, launches,
- * total_ms), clears the records and returns the row count.                                        */
+ * total_ms), clears the records and returns the row count.  While profiling is on, the backward pass
+ * keeps every kernel on the caller's stream (no side-stream overlap), so an interval is one kernel.   */
 int rnvp_prof_enable(int on);
 int rnvp_prof_collect(double* rows_host, int max_rows);
 
@@ -208,6 +209,20 @@ int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets
 int rnvp_dp_finalize(rnvp_plan* plan);
 /* sum-all-reduce `n` floats in place on `stream` (gradient buckets)         */
 int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream);
+
+/* ---- optimizer step ------------------------------------- *
+ * torch.optim.Adam(model.parameters(), lr, weight_decay) -- train.py:134, stepped at train.py:200 -- as one
+ * launch over all trainable tensors: coupled L2 weight decay, bias-corrected moments, optional clearing of
+ * the gradients.  Parameters are the caller's tensors (`params_host[i]`, `sizes_host[i]` floats each);
+ * gradient and the two moment buffers share one flat layout, segment i starting at `offsets_host[i]`.   */
+typedef struct rnvp_adam rnvp_adam;
+int rnvp_adam_create(void* const* params_host, const int64_t* offsets_host, const int64_t* sizes_host, int n,
+                     rnvp_adam** out);
+int rnvp_adam_destroy(rnvp_adam* a);
+/* `step` counts from 1 (the value torch keeps in state['step'] AFTER the update).                       */
+int rnvp_adam_step(rnvp_adam* a, float* flat_grad, float* exp_avg, float* exp_avg_sq, int64_t flat_len, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int64_t step, int zero_grad,
+                   void* stream);
 
 #ifdef __cplusplus
 }

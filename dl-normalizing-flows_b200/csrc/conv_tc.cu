@@ -169,7 +169,15 @@ constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
 constexpr int EPI_BOX_BYTES = 32 * 128;  // 32 rows x 32 fp32
 constexpr int EPI_BYTES_PER_WARP = 3 * EPI_BOX_BYTES;   // 1 residual + 2 output staging boxes
 constexpr int TC_MAX_STAGES = 4;
-template <int BN> struct TcCfg { static constexpr int STAGES = BN == 32 ? 3 : (BN == 64 ? 2 : 4); };
+// BN = 128 runs one CTA per SM: it gets eight epilogue warps (two per TMEM lane quarter, each owning half
+// of the column chunks) so that twice as many residual prefetches / result stores are in flight, and a
+// three-deep ring to pay for their staging buffers.  The narrower tiles keep four warps (two CTAs per SM).
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = BN == 32 ? 3 : (BN == 64 ? 2 : 3);
+  static constexpr int EPI_WARPS = BN == 128 ? 8 : 4;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int MIN_CTAS = BN == 128 ? 1 : 2;     // register cap: two CTAs of the narrow tiles per SM
+};
 
 struct ConvTcParams {
   const float* bias;
@@ -187,7 +195,7 @@ struct ConvTcParams {
 __device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmB,
                                                                    const __grid_constant__ CUtensorMap tmY,
                                                                    const __grid_constant__ CUtensorMap tmR,
@@ -203,10 +211,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
-  __shared__ __align__(8) uint64_t res_bar[4];
+  constexpr int EW = TcCfg<BN>::EPI_WARPS;
+  constexpr int CH_PER_WARP = (BN / 32) / (EW / 4) < 1 ? 1 : (BN / 32) / (EW / 4);   // column chunks per epilogue warp
+  __shared__ __align__(8) uint64_t res_bar[EW];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float red_sum[4][BN];
-  __shared__ float red_sq[4][BN];
+  __shared__ float red_sum[EW][BN];
+  __shared__ float red_sq[EW][BN];
   __shared__ __align__(16) float coef[2 * BN];  // (scale, shift) of the fused BN backward (n_tiles == 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -226,9 +236,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);        // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], EW);       // one arrive per epilogue warp
     }
-    for (int s = 0; s < 4; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < EW; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
@@ -299,20 +309,33 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
   } else {
     // ===================== epilogue =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    uint8_t* res_buf = epi_smem + q * EPI_BYTES_PER_WARP;
+    const int ew = warp - 2;                      // epilogue warp index
+    const int ci_lo = (ew >> 2) * CH_PER_WARP;    // first column chunk of this warp (two warps share a quarter)
+    uint8_t* res_buf = epi_smem + ew * EPI_BYTES_PER_WARP;
     uint8_t* out_buf = res_buf + EPI_BOX_BYTES;   // two boxes
-    float acc_s[BN / 32], acc_q[BN / 32];         // per-lane column sums (column c0 + lane), n_tiles == 1
+    float acc_s[CH_PER_WARP], acc_q[CH_PER_WARP]; // per-lane column sums (column c0 + lane), n_tiles == 1
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) acc_s[i] = acc_q[i] = 0.f;
+    for (int i = 0; i < CH_PER_WARP; ++i) acc_s[i] = acc_q[i] = 0.f;
     const bool keep_stats = prm.stats != nullptr;
     const int chunks_per_tile = min(BN / 32, ceil_div(prm.n, 32));   // column chunks that hold real channels
+    // first tile index >= tt0 (stride gridDim.x) of this CTA in which this warp owns a real column chunk
+    auto next_tile_with_work = [&](int tt0) {
+      for (; tt0 < num_tiles; tt0 += gridDim.x) {
+        const int tl = prm.rev ? num_tiles - 1 - tt0 : tt0;
+        if ((tl % prm.n_tiles) * BN + ci_lo * 32 < prm.n) break;
+      }
+      return tt0;
+    };
+    auto prefetch_res = [&](int tt_n, int chunk) {
+      const int tl = prm.rev ? num_tiles - 1 - tt_n : tt_n;
+      mbar_expect_tx(&res_bar[ew], EPI_BOX_BYTES);
+      tma_load_2d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (tl / prm.n_tiles) * 128 + q * 32);
+    };
     // residual prefetch of the first (tile, chunk) step of this warp
     int step = 0;
-    if (prm.has_res && lane == 0 && (int)blockIdx.x < num_tiles) {
-      const int t0 = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
-      const int m_tile = t0 / prm.n_tiles, n0 = (t0 % prm.n_tiles) * BN;
-      mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
-      tma_load_2d(res_buf, &tmR, &res_bar[q], n0, m_tile * 128 + q * 32);
+    if (prm.has_res && lane == 0) {
+      const int tt0 = next_tile_with_work(blockIdx.x);
+      if (tt0 < num_tiles) prefetch_res(tt0, ci_lo);
     }
     int ti = 0;
     for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x, ++ti) {
@@ -324,7 +347,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
       mbar_wait(&acc_full[as], (ti >> 1) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int ci = 0; ci < BN / 32; ++ci) {
+      for (int cl = 0; cl < CH_PER_WARP; ++cl) {
+        const int ci = ci_lo + cl;
         const int c0 = ci * 32;
         const int nb = n0 + c0;
         if (ci >= chunks_per_tile || nb >= prm.n) break;
@@ -344,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
         }
         float w2[32];                              // second statistic of the fused BN backward
         if (prm.has_res) {
-          mbar_wait(&res_bar[q], step & 1);
+          mbar_wait(&res_bar[ew], step & 1);
           if (!bnbwd) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -382,13 +406,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
           // the residual box is consumed: prefetch the one of the next step
           __syncwarp();
           if (lane == 0) {
-            int ntt = tt, nci = ci + 1;
-            if (nci >= chunks_per_tile || n0 + nci * 32 >= prm.n) { ntt = tt + gridDim.x; nci = 0; }
-            if (ntt < num_tiles) {
-              const int nt = prm.rev ? num_tiles - 1 - ntt : ntt;
-              const int nm = nt / prm.n_tiles, nn0 = (nt % prm.n_tiles) * BN;
-              mbar_expect_tx(&res_bar[q], EPI_BOX_BYTES);
-              tma_load_2d(res_buf, &tmR, &res_bar[q], nn0 + nci * 32, nm * 128 + q * 32);
+            // next step of THIS warp: its next chunk of the tile, else its first chunk of its next tile
+            const int nci = ci + 1;
+            if (cl + 1 < CH_PER_WARP && nci < chunks_per_tile && n0 + nci * 32 < prm.n) {
+              prefetch_res(tt, nci);
+            } else {
+              const int ntt = next_tile_with_work(tt + gridDim.x);
+              if (ntt < num_tiles) prefetch_res(ntt, ci_lo);
             }
           }
         }
@@ -438,8 +462,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
           }
           if (nb + lane >= prm.n) { s1 = 0.f; s2 = 0.f; }
           if (prm.n_tiles == 1) {
-            acc_s[ci] += s1;
-            acc_q[ci] += s2;
+            acc_s[cl] += s1;
+            acc_q[cl] += s2;
           } else if (nb + lane < prm.n) {
             atomicAdd(&prm.stats[nb + lane], (double)s1);
             atomicAdd(&prm.stats[prm.n + nb + lane], (double)s2);
@@ -453,17 +477,21 @@ __global__ void __launch_bounds__(TC_THREADS) conv_fwd_tf32_kernel(const __grid_
     }
     if (lane == 0) tma_store_wait_all();
     if (keep_stats && prm.n_tiles == 1) {
+      // every warp publishes a full row of BN partial sums (zero outside its own chunks)
+      for (int c = lane; c < BN; c += 32) { red_sum[ew][c] = 0.f; red_sq[ew][c] = 0.f; }
+      __syncwarp();
 #pragma unroll
-      for (int ci = 0; ci < BN / 32; ++ci) {
-        red_sum[q][ci * 32 + lane] = acc_s[ci];
-        red_sq[q][ci * 32 + lane] = acc_q[ci];
+      for (int cl = 0; cl < CH_PER_WARP; ++cl) {
+        red_sum[ew][(ci_lo + cl) * 32 + lane] = acc_s[cl];
+        red_sq[ew][(ci_lo + cl) * 32 + lane] = acc_q[cl];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const int tt = threadIdx.x - 64;
-      for (int c = tt; c < BN; c += 128) {
+      for (int c = tt; c < BN; c += 32 * EW) {
         if (c < prm.n) {
-          float s1 = red_sum[0][c] + red_sum[1][c] + red_sum[2][c] + red_sum[3][c];
-          float s2 = red_sq[0][c] + red_sq[1][c] + red_sq[2][c] + red_sq[3][c];
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < EW; ++w) { s1 += red_sum[w][c]; s2 += red_sq[w][c]; }
           atomicAdd(&prm.stats[c], (double)s1);
           atomicAdd(&prm.stats[prm.n + c], (double)s2);
         }
@@ -562,7 +590,8 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
     if (e && atoi(e) >= 1 && atoi(e) <= TC_MAX_STAGES) stages = atoi(e);
   }
   prm.stages = stages;
-  const int smem = stages * (A_TILE_BYTES + BN * 128) + 4 * EPI_BYTES_PER_WARP + 1024;
+  constexpr int THREADS = TcCfg<BN>::THREADS;
+  const int smem = stages * (A_TILE_BYTES + BN * 128) + TcCfg<BN>::EPI_WARPS * EPI_BYTES_PER_WARP + 1024;
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
     RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -573,10 +602,10 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
     cudaFuncAttributes fa;
     RNVP_CUDA(cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN>));
     const int by_smem = (228 * 1024) / (smem + (int)fa.sharedSizeBytes + 1024);
-    const int by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (TC_THREADS / 32));
+    const int by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
     const int by_tmem = 512 / (2 * BN < 32 ? 32 : 2 * BN);
     int occ = 0;
-    RNVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_tf32_kernel<BN>, TC_THREADS, smem));
+    RNVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_tf32_kernel<BN>, THREADS, smem));
     int c = by_smem < by_regs ? by_smem : by_regs;
     if (c > by_tmem) c = by_tmem;
     ctas_per_sm = c < 1 ? 1 : c;
@@ -591,7 +620,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tm
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas_per_sm;
   if (grid > tiles) grid = tiles;
-  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
+  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

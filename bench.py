@@ -166,7 +166,7 @@ def run_reference(args):
                             "sample": f"{n} steps of batch {batch} ({args.mode})"},
            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    _RECORD.append(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------
@@ -389,13 +389,32 @@ def run_b200(args):
                "achieved_tflops_algorithmic": value * tr_flops / 1e3,
                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                "kernel_time_ms_by_kind_per_step": by_kind, "kernel_classes": classes[:16]}
-        print(json.dumps(out))
+        _RECORD.append(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    # stdout carries exactly ONE line, the JSON record: anything a library prints there (NCCL's version banner,
+    # torchrun notices) is sent to stderr instead by swapping the descriptors for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+        if _RECORD:
+            print(_RECORD[-1], flush=True)
+
+
+_RECORD = []
+
+
+def _main(args):
     wd = int(os.environ.get("RNVP_BENCH_WATCHDOG", "0"))
     if wd:
         import faulthandler

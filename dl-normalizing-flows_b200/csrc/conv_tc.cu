@@ -49,6 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "WAIT_DONE:\n\t"
       "}" ::"r"(addr), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -67,6 +77,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -168,7 +182,16 @@ constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 e
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
 constexpr int EPI_BOX_BYTES = 32 * 128;  // 32 rows x 32 fp32
 constexpr int EPI_BYTES_PER_WARP = 3 * EPI_BOX_BYTES;   // 1 residual + 2 output staging boxes
-constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;
+// 3x3 "halo" mode (S >= 16): a CTA tile is an 8 x 16 pixel patch of one image.  Per 32-channel chunk ONE TMA
+// box of (8+2) x (16+2) pixels lands in shared memory (zero-filled outside the image) and all nine taps read
+// it through descriptors whose start address is shifted by whole 128-byte pixel rows: tcgen05 applies the
+// 128B swizzle to absolute shared-memory address bits (profiles/r01_probe_shifted_descriptor_windows.log),
+// so a row-shifted window of a swizzled TMA tile is a valid operand, with SBO = 10 pixels between the
+// 8-pixel row groups.  The activation tile is fetched once instead of nine times.
+constexpr int HALO_W = 10, HALO_H = 18;
+constexpr int HALO_TILE_BYTES = 23 * 1024;       // 180 rows x 128 B = 23040, rounded to the 1024-byte swizzle period
+constexpr int HALO_MAX_A_STAGES = 4;
 // BN = 128 runs one CTA per SM: it gets eight epilogue warps (two per TMEM lane quarter, each owning half
 // of the column chunks) so that twice as many residual prefetches / result stores are in flight, and a
 // three-deep ring to pay for their staging buffers.  The narrower tiles keep four warps (two CTAs per SM).
@@ -189,6 +212,11 @@ struct ConvTcParams {
   int m_tiles, n_tiles;
   int stages;                        // depth of the smem ring (<= TC_MAX_STAGES)
   int rev;                           // walk the tiles from the last to the first (L2 reuse, see next_sweep_dir)
+  int halo;                          // 3x3 halo mode: patch tiles, A ring of `a_stages` halo tiles, B ring of `stages`
+  int a_stages;
+  int diag;                          // timing diagnostics only (wrong results): 1 aligned start, 2 SBO 1024, 3 both
+  int b_tiles;                       // halo mode: weight tiles held in shared memory (ring depth, or 9 * kchunks resident)
+  int tiles_x, tiles_per_img;        // halo mode: patches per image row / per image
 };
 
 // byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
@@ -206,9 +234,14 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  // flat mode: ring of (A tile + B tile) stages.  halo mode: A ring of halo tiles, then a B ring of weight tiles
+  uint8_t* b_ring = smem + prm.a_stages * HALO_TILE_BYTES;
+  uint8_t* epi_smem = prm.halo ? b_ring + prm.b_tiles * B_TILE_BYTES : smem + STAGES * STAGE_BYTES;
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_full[HALO_MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t a_empty[HALO_MAX_A_STAGES];
+  __shared__ __align__(8) uint64_t bres_bar;          // halo mode 2: all weight tiles of this CTA's n-tile are resident
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
   constexpr int EW = TcCfg<BN>::EPI_WARPS;
@@ -234,6 +267,11 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int s = 0; s < HALO_MAX_A_STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(&bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], EW);       // one arrive per epilogue warp
@@ -260,7 +298,61 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane == 0 && prm.halo) {
+      // The halo tiles run ahead of the weight tiles: chunk g + (a_stages - 1) is requested while the weights
+      // of chunk g are still being issued, as soon as its ring slot is free (non-blocking test), so that the
+      // 180-row activation box is in flight for a whole chunk of MMAs before it is needed.
+      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+      const int total_chunks = my_tiles * prm.kchunks;
+      int a_issued = 0;
+      auto issue_a = [&](bool block) -> bool {
+        if (a_issued >= total_chunks) return false;
+        const int as = a_issued % prm.a_stages;
+        const uint32_t par = ((a_issued / prm.a_stages) & 1) ^ 1;
+        if (block) mbar_wait(&a_empty[as], par);
+        else if (!mbar_test(&a_empty[as], par)) return false;
+        const int tt = blockIdx.x + (a_issued / prm.kchunks) * gridDim.x, kc = a_issued % prm.kchunks;
+        const int t = prm.rev ? num_tiles - 1 - tt : tt;
+        const int m_tile = t / prm.n_tiles;
+        const int img0 = m_tile / prm.tiles_per_img, r = m_tile % prm.tiles_per_img;
+        const int row0 = (r / prm.tiles_x) * 16, col0 = (r % prm.tiles_x) * 8;
+        if (prm.diag & 4) {
+          mbar_expect_tx(&a_full[as], 0);            // timing diagnostic: no activation load at all
+        } else {
+          mbar_expect_tx(&a_full[as], HALO_W * HALO_H * 128);
+          tma_load_4d(smem + as * HALO_TILE_BYTES, &tmA, &a_full[as], kc * 32, col0 - 1, row0 - 1, img0);
+        }
+        ++a_issued;
+        return true;
+      };
+      if (prm.halo == 2) {
+        // resident weights: the CTA keeps one n-tile for its whole life (gridDim.x is a multiple of n_tiles)
+        if (my_tiles > 0) {
+          const int t0 = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+          const int n0 = (t0 % prm.n_tiles) * BN;
+          mbar_expect_tx(&bres_bar, 9 * prm.kchunks * B_TILE_BYTES);
+          for (int kc = 0; kc < prm.kchunks; ++kc)
+            for (int tap = 0; tap < 9; ++tap)
+              tma_load_3d(b_ring + (kc * 9 + tap) * B_TILE_BYTES, &tmB, &bres_bar, kc * 32, n0, tap);
+        }
+        while (issue_a(true)) {}
+      } else {
+        int bi = 0;
+        for (int g = 0; g < total_chunks; ++g) {
+          const int tt = blockIdx.x + (g / prm.kchunks) * gridDim.x, kc = g % prm.kchunks;
+          const int t = prm.rev ? num_tiles - 1 - tt : tt;
+          const int n0 = (t % prm.n_tiles) * BN;
+          while (a_issued <= g) issue_a(true);
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            if (a_issued < g + prm.a_stages) issue_a(false);
+            const int s = bi % STAGES;
+            mbar_wait(&empty_bar[s], ((bi / STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full_bar[s], B_TILE_BYTES);
+            tma_load_3d(b_ring + s * B_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+          }
+        }
+      }
+    } else if (lane == 0) {
       const int hw = prm.S * prm.S;
       int it_glob = 0;
       for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x) {
@@ -283,7 +375,47 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && prm.halo) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+      int ai = 0, bi = 0, ti = 0;
+      if (prm.halo == 2 && (int)blockIdx.x < num_tiles) {
+        mbar_wait(&bres_bar, 0);
+        tc_fence_after();
+      }
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+        const int as_acc = ti & 1;
+        mbar_wait(&acc_empty[as_acc], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as_acc * BN);
+        for (int kc = 0; kc < prm.kchunks; ++kc, ++ai) {
+          const int as = ai % prm.a_stages;
+          mbar_wait(&a_full[as], (ai / prm.a_stages) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + as * HALO_TILE_BYTES);
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            // window of tap (dy,dx) = (tap/3-1, tap%3-1): shifted by (dy+1) halo rows and (dx+1) pixels
+            const uint32_t a_tap = a_addr + ((prm.diag & 1) ? 0u : (uint32_t)(((tap / 3) * HALO_W + tap % 3) * 128));
+            const uint32_t a_sbo = (prm.diag & 2) ? 1024u : (uint32_t)(HALO_W * 128);
+            uint32_t b_addr;
+            const int s = bi % STAGES;
+            if (prm.halo == 2) {
+              b_addr = smem_u32(b_ring + (kc * 9 + tap) * B_TILE_BYTES);
+            } else {
+              mbar_wait(&full_bar[s], (bi / STAGES) & 1);
+              tc_fence_after();
+              b_addr = smem_u32(b_ring + s * B_TILE_BYTES);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_tf32(d_tmem, make_desc(a_tap + k * 32, 16, a_sbo), make_desc(b_addr + k * 32, 16, 1024), idesc,
+                        (kc | tap | k) != 0);
+            if (prm.halo != 2) umma_commit(&empty_bar[s]);   // weight tile free once these MMAs retire
+          }
+          umma_commit(&a_empty[as]);              // halo tile free once all nine taps have read it
+        }
+        umma_commit(&acc_full[as_acc]);
+      }
+    } else if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       int it_glob = 0, ti = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
@@ -317,6 +449,8 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
 #pragma unroll
     for (int i = 0; i < CH_PER_WARP; ++i) acc_s[i] = acc_q[i] = 0.f;
     const bool keep_stats = prm.stats != nullptr;
+    // per-channel sums can stay in registers across tiles when the CTA never changes its n-tile
+    const bool own_ntile = prm.n_tiles == 1 || prm.halo == 2;
     const int chunks_per_tile = min(BN / 32, ceil_div(prm.n, 32));   // column chunks that hold real channels
     // first tile index >= tt0 (stride gridDim.x) of this CTA in which this warp owns a real column chunk
     auto next_tile_with_work = [&](int tt0) {
@@ -329,7 +463,13 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     auto prefetch_res = [&](int tt_n, int chunk) {
       const int tl = prm.rev ? num_tiles - 1 - tt_n : tt_n;
       mbar_expect_tx(&res_bar[ew], EPI_BOX_BYTES);
-      tma_load_2d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (tl / prm.n_tiles) * 128 + q * 32);
+      if (prm.halo) {                     // 32 TMEM lanes of this warp = 4 patch rows x 8 pixels
+        const int mt = tl / prm.n_tiles, r = mt % prm.tiles_per_img;
+        tma_load_4d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (r % prm.tiles_x) * 8,
+                    (r / prm.tiles_x) * 16 + q * 4, mt / prm.tiles_per_img);
+      } else {
+        tma_load_2d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (tl / prm.n_tiles) * 128 + q * 32);
+      }
     };
     // residual prefetch of the first (tile, chunk) step of this warp
     int step = 0;
@@ -426,7 +566,12 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(ob, &tmY, nb, prow0);              // rows >= P and columns >= n are clipped by the map
+          if (prm.halo) {
+            const int r = m_tile % prm.tiles_per_img;
+            tma_store_4d(ob, &tmY, nb, (r % prm.tiles_x) * 8, (r / prm.tiles_x) * 16 + q * 4, m_tile / prm.tiles_per_img);
+          } else {
+            tma_store_2d(ob, &tmY, nb, prow0);            // rows >= P and columns >= n are clipped by the map
+          }
           tma_store_commit();
         }
         ++step;
@@ -461,7 +606,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
             s2 = warp_transpose_sum(wsum, lane);
           }
           if (nb + lane >= prm.n) { s1 = 0.f; s2 = 0.f; }
-          if (prm.n_tiles == 1) {
+          if (own_ntile) {
             acc_s[cl] += s1;
             acc_q[cl] += s2;
           } else if (nb + lane < prm.n) {
@@ -476,7 +621,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
     }
     if (lane == 0) tma_store_wait_all();
-    if (keep_stats && prm.n_tiles == 1) {
+    if (keep_stats && own_ntile) {
       // every warp publishes a full row of BN partial sums (zero outside its own chunks)
       for (int c = lane; c < BN; c += 32) { red_sum[ew][c] = 0.f; red_sq[ew][c] = 0.f; }
       __syncwarp();
@@ -487,13 +632,15 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const int tt = threadIdx.x - 64;
+      const int t_first = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      const int n0_cta = (t_first % prm.n_tiles) * BN;       // the n-tile this CTA kept for all its tiles
       for (int c = tt; c < BN; c += 32 * EW) {
-        if (c < prm.n) {
+        if (n0_cta + c < prm.n) {
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int w = 0; w < EW; ++w) { s1 += red_sum[w][c]; s2 += red_sq[w][c]; }
-          atomicAdd(&prm.stats[c], (double)s1);
-          atomicAdd(&prm.stats[prm.n + c], (double)s2);
+          atomicAdd(&prm.stats[n0_cta + c], (double)s1);
+          atomicAdd(&prm.stats[prm.n + n0_cta + c], (double)s2);
         }
       }
     }
@@ -572,54 +719,116 @@ static int make_row_map(CUtensorMap* m, const float* base, int P, int n, int ld)
   return encode_map(m, base, 2, dims, strides, box);
 }
 
+// 4-D map over a [B][S][S][ld] fp32 tensor exposing `n` real channels, (32 ch, 8, 4, 1) boxes: the 32 TMEM
+// lanes one epilogue warp owns in halo mode (4 patch rows x 8 pixels)
+static int make_patch_map(CUtensorMap* m, const float* base, int B, int S, int n, int ld) {
+  cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4};
+  cuuint32_t box[4] = {32, 8, 4, 1};
+  return encode_map(m, base, 4, dims, strides, box);
+}
+
+// Opt-in (RNVP_HALO=1).  The path is correct (tests/test_gpu_ops.py::test_conv_tf32_halo) and cuts the
+// shared-memory feed of a 3x3 conv by 2-3x, but measured on B200 it is NOT faster than nine tap-shifted
+// loads: with <= 128 output channels these convs are bound by the tcgen05.mma issue rate -- an M=128, K=8
+// kind::tf32 instruction occupies the tensor pipe for ~100 cycles however small N is (36 MMAs of N=32 per
+// 128-pixel tile = 1.9 us, exactly the measured 108 us per S=64 launch) -- not by the operand feed.  The
+// resident-weight variant runs one CTA per SM and loses the overlap two CTAs give.  See DESIGN.md 4.
+static bool halo_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_HALO");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on != 0;
+}
+// 3x3 convs on feature maps of at least 16 x 16 (sides a multiple of 16) take the halo path
+static bool use_halo(const ConvArgs& a) { return halo_enabled() && a.taps == 9 && a.S >= 16 && a.S % 16 == 0; }
+
 template <int BN>
-static int launch_fwd(const ConvArgs& a, ConvTcParams prm, const CUtensorMap& tmA, cudaStream_t st) {
-  CUtensorMap tmB, tmY, tmR;
+static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
+  CUtensorMap tmA, tmB, tmY, tmR;
+  const bool halo = use_halo(a);
+  int bw = 0, bh = 0, bn = 0;
+  pixel_box(a.S, 128, &bw, &bh, &bn);
+  if (halo) RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, HALO_W, HALO_H, 1));
+  else RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
   cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
   cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
-  RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
-  if (a.bn_x) RNVP_TRY(make_row_map(&tmR, a.bn_x, prm.P, a.n, a.ldy));
-  else if (a.res) RNVP_TRY(make_row_map(&tmR, a.res, prm.P, a.n, a.ldy));
-  else tmR = tmY;
-  static int stages = 0;
-  if (!stages) {
-    stages = TcCfg<BN>::STAGES;
-    const char* e = getenv(BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
-    if (e && atoi(e) >= 1 && atoi(e) <= TC_MAX_STAGES) stages = atoi(e);
+  const float* rsrc = a.bn_x ? a.bn_x : a.res;
+  if (halo) {
+    RNVP_TRY(make_patch_map(&tmY, a.y, a.B, a.S, a.n, a.ldy));
+    if (rsrc) RNVP_TRY(make_patch_map(&tmR, rsrc, a.B, a.S, a.n, a.ldy));
+  } else {
+    RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
+    if (rsrc) RNVP_TRY(make_row_map(&tmR, rsrc, prm.P, a.n, a.ldy));
   }
-  prm.stages = stages;
+  if (!rsrc) tmR = tmY;
   constexpr int THREADS = TcCfg<BN>::THREADS;
-  const int smem = stages * (A_TILE_BYTES + BN * 128) + TcCfg<BN>::EPI_WARPS * EPI_BYTES_PER_WARP + 1024;
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-    // resident CTAs per SM from the kernel's own footprint: shared memory (dynamic + static + 1 KB the
-    // driver reserves per CTA) against the 228 KB of an SM, registers against the 64 K file, TMEM columns
+  constexpr int EPI = TcCfg<BN>::EPI_WARPS * EPI_BYTES_PER_WARP;
+  // shared-memory plan of this launch.  mode 0 flat: ring of (A + B) stages.  mode 1 halo, streamed weights:
+  // A ring of halo tiles + B ring (BN = 32 keeps two CTAs per SM, the wider tiles run one).  mode 2 halo,
+  // resident weights (BN = 32, <= 64 input channels): all 9 * kchunks weight tiles of the CTA's n-tile stay in
+  // shared memory, one CTA per SM, a deeper A ring.
+  const int kchunks = a.kpad / 32;
+  const int mode = !halo ? 0 : (BN == 32 && kchunks <= 2 ? 2 : 1);
+  static int flat_stages = 0;
+  static int by_regs = 0, static_smem = 0;
+  if (!flat_stages) {
+    flat_stages = TcCfg<BN>::STAGES;
+    const char* e = getenv(BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
+    if (e && atoi(e) >= 1 && atoi(e) <= TC_MAX_STAGES) flat_stages = atoi(e);
     cudaFuncAttributes fa;
     RNVP_CUDA(cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN>));
-    const int by_smem = (228 * 1024) / (smem + (int)fa.sharedSizeBytes + 1024);
-    const int by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
-    const int by_tmem = 512 / (2 * BN < 32 ? 32 : 2 * BN);
-    int occ = 0;
-    RNVP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_fwd_tf32_kernel<BN>, THREADS, smem));
-    int c = by_smem < by_regs ? by_smem : by_regs;
-    if (c > by_tmem) c = by_tmem;
-    ctas_per_sm = c < 1 ? 1 : c;
-    if (const char* e = getenv("RNVP_TC_CTAS")) { if (atoi(e) >= 1) ctas_per_sm = atoi(e); }
-    if (getenv("RNVP_DEBUG"))
-      fprintf(stderr, "[rnvp] conv_fwd_tf32<%d>: stages %d smem %d+%d regs %d -> by_smem %d by_regs %d by_tmem %d "
-              "(occupancy API %d) => %d CTAs/SM\n", BN, stages, smem, (int)fa.sharedSizeBytes, fa.numRegs, by_smem,
-              by_regs, by_tmem, occ, ctas_per_sm);
+    by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
+    static_smem = (int)fa.sharedSizeBytes;
+    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   227 * 1024 - static_smem));
+    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
   }
+  int smem;
+  if (mode == 0) {
+    prm.stages = flat_stages; prm.a_stages = 0; prm.b_tiles = 0;
+    smem = flat_stages * (A_TILE_BYTES + BN * 128) + EPI + 1024;
+  } else if (mode == 1) {
+    prm.a_stages = BN == 64 ? 3 : 2;
+    prm.stages = BN == 32 ? 3 : (BN == 64 ? 8 : 4);
+    prm.b_tiles = prm.stages;
+    smem = prm.a_stages * HALO_TILE_BYTES + prm.b_tiles * BN * 128 + EPI + 1024;
+  } else {
+    prm.a_stages = kchunks == 1 ? 4 : 3;
+    prm.stages = 1;
+    prm.b_tiles = 9 * kchunks;
+    smem = prm.a_stages * HALO_TILE_BYTES + prm.b_tiles * BN * 128 + EPI + 1024;
+  }
+  RNVP_REQUIRE(smem + static_smem <= 227 * 1024, "conv: shared-memory plan of %d bytes does not fit", smem);
+  // resident CTAs per SM from the kernel's own footprint: shared memory (dynamic + static + 1 KB the driver
+  // reserves per CTA) against the 228 KB of an SM, registers against the 64 K file, TMEM columns
+  // (cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports this kernel: it answered 1 where 2 fit)
+  int ctas = (228 * 1024) / (smem + static_smem + 1024);
+  if (ctas > by_regs) ctas = by_regs;
+  if (ctas > 512 / (2 * BN < 32 ? 32 : 2 * BN)) ctas = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+  if (ctas < 1) ctas = 1;
+  if (const char* e2 = getenv("RNVP_TC_CTAS")) { if (atoi(e2) >= 1) ctas = atoi(e2); }
+  static bool said[3] = {false, false, false};
+  if (!said[mode] && getenv("RNVP_DEBUG")) {
+    said[mode] = true;
+    fprintf(stderr, "[rnvp] conv_fwd_tf32<%d> mode %d: A stages %d, B tiles %d, smem %d+%d, regs -> %d, => %d CTAs/SM\n", BN,
+            mode, prm.a_stages, mode ? prm.b_tiles : prm.stages, smem, static_smem, by_regs, ctas);
+  }
+  prm.halo = mode;
+  { const char* e3 = getenv("RNVP_HALO_DIAG"); prm.diag = e3 ? atoi(e3) : 0; }
+  prm.tiles_x = a.S / 8;
+  prm.tiles_per_img = (a.S / 8) * (a.S / 16);
   prm.m_tiles = ceil_div(prm.P, 128);
   prm.n_tiles = ceil_div(a.n, BN);
   int tiles = prm.m_tiles * prm.n_tiles;
-  int grid = kNumSMs * ctas_per_sm;
+  int grid = kNumSMs * ctas;
   if (grid > tiles) grid = tiles;
+  if (mode == 2) grid -= grid % prm.n_tiles;          // a CTA must keep one n-tile: its weights are resident
   RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
@@ -643,17 +852,18 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "conv: taps=%d", a.taps);
   RNVP_REQUIRE(((uintptr_t)a.x & 15) == 0 && ((uintptr_t)a.w & 15) == 0 && ((uintptr_t)a.y & 15) == 0,
                "conv operands must be 16-byte aligned");
-  CUtensorMap tmA;
-  RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
   ConvTcParams prm{};
   prm.bias = a.bias; prm.has_res = a.res != nullptr || a.bn_x != nullptr; prm.stats = a.stats;
   prm.bn_save = a.bn_x ? a.bn_save : nullptr;
   prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
   prm.rev = next_sweep_dir();
-  if (a.n <= 32) return launch_fwd<32>(a, prm, tmA, st);
-  if (a.n <= 64) return launch_fwd<64>(a, prm, tmA, st);
-  return launch_fwd<128>(a, prm, tmA, st);
+  if (a.n <= 32) return launch_fwd<32>(a, prm, st);
+  // 3x3 halo convs with <= 64 input and output channels: two 32-wide n-tiles with resident weights beat one
+  // 64-wide tile with streamed weights (the weight tiles, not the activations, dominate the smem feed)
+  if (a.n <= 64 && use_halo(a) && a.kpad <= 64) return launch_fwd<32>(a, prm, st);
+  if (a.n <= 64) return launch_fwd<64>(a, prm, st);
+  return launch_fwd<128>(a, prm, st);
 }
 
 // ---------------------------------------------------------------------------------------------

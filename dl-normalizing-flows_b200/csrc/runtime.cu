@@ -492,9 +492,19 @@ int net_forward(const Ctx& c, int ci, int training) {
   };
   auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
   const ConvDesc* cv = d.convs.data();
+  // The skip path (in_skip and the core_skips, accumulated into `skip`) is off the critical chain of the
+  // trunk: with the side stream active (training mode 2, every a_i has its own buffer) those five convs
+  // overlap the residual blocks and are joined before out_block's batch norm.
+  auto skip_conv = [&](const ConvDesc& cvs, const float* x, const float* res, double* stats) -> int {
+    if (!c.side_on) return run_conv(c, cvs, false, x, S, c.act(ci, A.skip), ld, bias(cvs), res, stats);
+    RNVP_TRY(fork_to_side(c));
+    Ctx cs2 = c;
+    cs2.st = c.wst;
+    return run_conv(cs2, cvs, false, x, S, c.act(ci, A.skip), ld, bias(cvs), res, stats);
+  };
   // a0 = in_block(h0); skip = in_skip(a0)
   RNVP_TRY(run_conv(c, cv[0], false, c.act(ci, A.h0), S, c.act(ci, A.a[0]), ld, bias(cv[0]), nullptr, st_of(0)));
-  RNVP_TRY(run_conv(c, cv[1], false, c.act(ci, A.a[0]), S, c.act(ci, A.skip), ld, bias(cv[1]), nullptr, nullptr));
+  RNVP_TRY(skip_conv(cv[1], c.act(ci, A.a[0]), nullptr, nullptr));
   for (int i = 0; i < R; ++i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
     float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
@@ -504,9 +514,9 @@ int net_forward(const Ctx& c, int ci, int training) {
     RNVP_TRY(run_conv(c, *rb3, false, H, S, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2)));
     RNVP_TRY(bn(3 * i + 2, c.act(ci, A.u2[i])));
     RNVP_TRY(run_conv(c, *rb6, false, H, S, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr));
-    RNVP_TRY(run_conv(c, *cs, false, an, S, c.act(ci, A.skip), ld, bias(*cs), c.act(ci, A.skip),
-                      i == R - 1 ? st_of(3 * R) : nullptr));
+    RNVP_TRY(skip_conv(*cs, an, c.act(ci, A.skip), i == R - 1 ? st_of(3 * R) : nullptr));
   }
+  RNVP_TRY(join_side(c));
   RNVP_TRY(bn(3 * R, c.act(ci, A.skip)));
   const ConvDesc& oc = cv[2 + 4 * R];
   RNVP_TRY(run_conv(c, oc, false, H, S, c.act(ci, A.st), d.cst_pad, bias(oc), nullptr, nullptr));

@@ -110,6 +110,15 @@ class Adam(torch.optim.Optimizer):
             return
         eng._flat_grad.zero_()
 
+    def state_dict(self):
+        """torch's layout; every entry gets its own ``step`` tensor and its own copy of the moments (internally
+        the step counter is one shared object and the moments are views of two flat buffers, which torch's
+        multi-tensor Adam must not inherit through ``load_state_dict``)."""
+        sd = super().state_dict()
+        sd["state"] = {k: {"step": v["step"].clone(), "exp_avg": v["exp_avg"].clone(),
+                           "exp_avg_sq": v["exp_avg_sq"].clone()} for k, v in sd["state"].items()}
+        return sd
+
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
         self._sig = None                   # re-flatten the loaded moments at the next step

@@ -159,9 +159,29 @@ def test_conv_fp32(pkg, shape):
 
 @pytest.mark.parametrize("shape", [(2, 8, 7, 32, 3), (3, 4, 32, 32, 1), (2, 16, 64, 6, 1), (1, 4, 97, 64, 3),
                                    (5, 2, 12, 8, 3), (2, 64, 32, 32, 3), (4, 8, 256, 512, 1), (2, 32, 64, 64, 3),
-                                   (3, 8, 160, 96, 3), (40, 4, 512, 512, 1)])
+                                   (3, 8, 160, 96, 3), (40, 4, 512, 512, 1),
+                                   (2, 16, 128, 128, 3), (3, 16, 25, 128, 3), (2, 64, 7, 32, 3), (1, 32, 13, 64, 3)])
 def test_conv_tf32(pkg, shape):
     """tcgen05 kind::tf32 implicit GEMM (TMA-fed, TMEM accumulator) vs the fp32 torch reference."""
     B, S, cin, cout, k = shape
     _conv_case(pkg, B, S, cin, cout, k, 1)
     _conv_case(pkg, B, S, cin, cout, k, 1, seed=1, with_res=False)
+
+
+HALO_SHAPES = [(2, 64, 32, 32, 3), (2, 32, 64, 64, 3), (2, 16, 128, 128, 3), (3, 16, 25, 128, 3), (2, 64, 7, 32, 3),
+               (1, 32, 13, 64, 3)]
+
+
+def test_conv_tf32_halo():
+    """The opt-in 3x3 halo path (RNVP_HALO=1, read once per process): one haloed activation tile per 32-channel
+    chunk, the nine taps through row-shifted shared-memory descriptors; streamed and resident weight tiles."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, importlib; sys.path[:0] = [%r, %r]; import conftest; "
+            "pkg = importlib.import_module('dl-normalizing-flows_b200'); import test_gpu_ops as T; "
+            "[T._conv_case(pkg, *s, 1) for s in T.HALO_SHAPES]; print('halo ok')"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    env = dict(os.environ, RNVP_HALO="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "halo ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

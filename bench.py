@@ -176,8 +176,12 @@ def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
     """Algorithmic traffic / flops of one profiled launch class (fp32 NHWC, every operand once)."""
     pad = lambda v, m: (v + m - 1) // m * m
     P = B * S * S
-    if kind in (0, 1):          # conv / dgrad: read input rows, write output rows, read weights
-        byt = 4 * (P * pad(cin, 32) + P * cout + taps * pad(cout, 16) * pad(cin, 32))
+    if kind == 0:               # conv: read input rows, write output rows, read weights (a residual read, where the
+        byt = 4 * (P * pad(cin, 32) + P * cout + taps * pad(cout, 16) * pad(cin, 32))     # layer has one, is not counted)
+        flops = 2.0 * P * cin * cout * taps
+    elif kind == 1:             # dgrad: as conv, plus the second input every dgrad of the stack reads -- the saved pre-BN
+        # activation of the fused ReLU/BN-backward epilogue, or the running gradient it accumulates into
+        byt = 4 * (P * pad(cin, 32) + 2 * P * cout + taps * pad(cout, 16) * pad(cin, 32))
         flops = 2.0 * P * cin * cout * taps
     elif kind == 2:             # wgrad: read x rows and dy rows, write dw
         byt = 4 * (P * pad(cin, 32) + P * pad(cout, 32) + taps * pad(cout, 16) * pad(cin, 32))
@@ -241,11 +245,14 @@ def run_b200(args):
 
     net.train(args.mode == "train")
     if args.mode == "sample":
-        # converged running statistics first (a sampler is used after training)
+        # converged running statistics first (a sampler is used after training); the training workspace of the
+        # full sampling batch would not fit, so these steps use at most 256 images
         net.train()
         for _ in range(3):
-            train_step(dev_u8)
+            train_step(dev_u8[:256])
         net.eval()
+        opt.zero_grad(set_to_none=True)
+        net.engine().release_workspaces()
     step = train_step if args.mode == "train" else sample_step
 
     def barrier():
@@ -357,6 +364,13 @@ def run_b200(args):
                 roof["avg_us"] = dur * 1e6
                 roof["share_of_profiled_kernel_time"] = top["ms"] / tot
                 roof["peak_source"] = peaks["src"]
+                roof["schedule"] = ("durations taken with every kernel on one stream (rnvp_prof_enable switches the "
+                                    "wgrad side stream off), CUDA events around each launch")
+                try:                                          # DRAM bytes per launch from the committed ncu capture
+                    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                        roof["traffic"] = json.load(f).get(roof["kernel"])
+                except Exception:
+                    pass
                 roof["algorithmic_bytes_per_launch"] = byt
                 roof["algorithmic_flops_per_launch"] = fl
 

@@ -185,6 +185,11 @@ class Engine:
             self._ws[mode] = ws
         return ws
 
+    def release_workspaces(self) -> None:
+        """Drop the cached workspaces (e.g. the training layout before a large sampling batch)."""
+        for k in self._ws:
+            self._ws[k] = None
+
     # -- gradient installation ------------------------------------------------------ #
     def prepare_grads(self) -> None:
         """Make ``param.grad`` of every trainable parameter alias its view of the flat buffer.

@@ -1072,40 +1072,66 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 
 // grid (pad32(max_cout), njobs); v is (cout, cin, taps) with taps innermost (NCHW-style weight).
 // Block `co` writes row co of wf and column co of wb completely, zeros included.
-__global__ void weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase, int rnd) {
-  __shared__ float sm[8];
+// One block = (job, tile of 32 output channels).  Phase 1: the 32 row norms (a warp per row, coalesced).
+// Phase 2, per tile of 32 input channels: the contiguous [32 co][32 ci * taps] slab of v goes through shared
+// memory so that BOTH layouts are written with full 128-byte rows -- wf[tap][co][ci] along ci, the
+// transposed and tap-flipped wb[taps-1-tap][ci][co] along co.  Padding rows / columns are written as zeros.
+constexpr int kWnTile = 32;
+__global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase, int rnd) {
+  extern __shared__ float wn_sm[];               // [32][32 * taps + 1] slab, then f[32]
   const WnJob j = jobs[blockIdx.y];
-  const int co = blockIdx.x;
-  if (co >= j.kpad_b) return;                    // kpad_b = pad32(cout) >= npad_f
-  const bool valid = co < j.cout;
-  const int per = j.cin * j.taps;
-  const float* v = j.v + (int64_t)(valid ? co : 0) * per;
-  float f = 0.f;
-  if (valid) {
+  const int co0 = blockIdx.x * kWnTile;
+  if (co0 >= j.kpad_b) return;                   // kpad_b = pad32(cout) >= npad_f
+  const int taps = j.taps, per = j.cin * taps;
+  const int pitch = kWnTile * taps + 1;
+  float* slab = wn_sm;
+  float* f = wn_sm + kWnTile * pitch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kWnTile; r += 8) {
+    const int co = co0 + r;
     float ss = 0.f;
-    for (int e = threadIdx.x; e < per; e += blockDim.x) ss += v[e] * v[e];
-    ss = block_sum(ss, sm);
-    f = j.g[co] / sqrtf(ss);
+    if (co < j.cout) {
+      const float* v = j.v + (int64_t)co * per;
+      for (int e = lane; e < per; e += 32) ss = fmaf(v[e], v[e], ss);
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) f[r] = co < j.cout ? j.g[co] / sqrtf(ss) : 0.f;
   }
   float* wf = wbase + j.wf_off;
   float* wb = wbase + j.wb_off;
-  if (co < j.npad_f) {
-    for (int e = threadIdx.x; e < j.taps * j.kpad_f; e += blockDim.x) {
-      int tap = e / j.kpad_f, ci = e % j.kpad_f;
-      wf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci] =
-          (valid && ci < j.cin) ? maybe_round(v[ci * j.taps + tap] * f, rnd) : 0.f;
+  for (int ci0 = 0; ci0 < j.kpad_f; ci0 += kWnTile) {
+    __syncthreads();                             // f ready / previous slab consumed
+    const int ncols = min(kWnTile, j.cin - ci0) * taps;            // real floats per row in this slab (<= 0: none)
+    for (int r = warp; r < kWnTile; r += 8) {
+      const int co = co0 + r;
+      const float* v = j.v + (int64_t)co * per + (int64_t)ci0 * taps;
+      for (int e = lane; e < kWnTile * taps; e += 32)
+        slab[r * pitch + e] = (co < j.cout && e < ncols) ? v[e] : 0.f;
     }
-  }
-  for (int e = threadIdx.x; e < j.taps * j.npad_b; e += blockDim.x) {
-    int tap = e / j.npad_b, ci = e % j.npad_b;
-    wb[((int64_t)(j.taps - 1 - tap) * j.npad_b + ci) * j.kpad_b + co] =
-        (valid && ci < j.cin) ? maybe_round(v[ci * j.taps + tap] * f, rnd) : 0.f;
+    __syncthreads();
+    for (int tap = 0; tap < taps; ++tap) {
+      // wf[tap][co0 + r][ci0 + lane]: a warp writes one 128-byte row
+      for (int r = warp; r < kWnTile; r += 8) {
+        const int co = co0 + r;
+        if (co < j.npad_f)
+          wf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci0 + lane] = maybe_round(slab[r * pitch + lane * taps + tap] * f[r], rnd);
+      }
+      // wb[taps-1-tap][ci0 + i][co0 + lane]
+      for (int i = warp; i < kWnTile; i += 8) {
+        const int ci = ci0 + i;
+        if (ci < j.npad_b)
+          wb[((int64_t)(taps - 1 - tap) * j.npad_b + ci) * j.kpad_b + co0 + lane] =
+              maybe_round(slab[lane * pitch + i * taps + tap] * f[lane], rnd);
+      }
+    }
   }
 }
 int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
                      cudaStream_t st) {
   if (njobs == 0) return RNVP_OK;
-  weightnorm_fwd_kernel<<<dim3(pad_to(max_cout, 32), njobs), 128, 0, st>>>(jobs_dev, wbase, tf32_round);
+  // the slab is sized for 3x3 kernels (the only other tap count is 1)
+  const int smem = (kWnTile * (kWnTile * 9 + 1) + kWnTile) * (int)sizeof(float);
+  weightnorm_fwd_kernel<<<dim3(ceil_div(pad_to(max_cout, 32), kWnTile), njobs), 256, smem, st>>>(jobs_dev, wbase, tf32_round);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

@@ -1265,6 +1265,7 @@ int rnvp_restore(const float* on, const float* off, float* x, int B, int C, int 
 int rnvp_weightnorm_forward(const float* v, const float* g, float* wf, float* wb, int cout, int cin, int ksize,
                             void* stream) {
   RNVP_REQUIRE(wf && wb, "both operand layouts are produced; pass two buffers");
+  RNVP_REQUIRE(ksize == 1 || ksize == 3, "weight norm: kernel size %d unsupported (1 or 3)", ksize);
   cudaStream_t st = (cudaStream_t)stream;
   WnJob j{};
   j.v = v; j.g = g;

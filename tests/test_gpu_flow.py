@@ -276,3 +276,54 @@ def test_lean_and_fast_training_modes_agree(pkg, golden_dir):
     # amplifies like any other 1e-7 perturbation: same gate as against the reference
     grel, worst, wk = compare_grads(out[2][1], {k: v.cpu() for k, v in out[1][1].items()})
     assert grel < 2e-2, (grel, worst, wk)
+
+
+def _grad_dump(path):
+    """Helper run in a subprocess: one train-mode forward + backward of a fixed model, gradients to `path`."""
+    import importlib
+    pkg = importlib.import_module("dl-normalizing-flows_b200")
+    c = dict(channels=3, image=32, base_dim=32, res_blocks=2, num_scales=3, seed=11)
+    st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
+    m = build(pkg, c, st0, "fp32")
+    m.train()
+    x = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(5)).to(DEV)
+    out = {}
+    for rep in range(2):                      # twice: the second pass reuses every scratch buffer and event
+        m.zero_grad()
+        ll, ws = m(x)
+        (-ll.mean() + 5e-5 * ws).backward()
+        torch.cuda.synchronize()
+        out[rep] = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters() if p.grad is not None}
+        out[f"ll{rep}"] = ll.detach().cpu()
+    torch.save(out, path)
+
+
+def test_streams_and_pdl_do_not_change_results(tmp_path):
+    """The side-stream wgrads (two scratch sets, event fork/join) and programmatic dependent launch are pure
+    scheduling: gradients must equal those of the plain single-stream, fully serialised schedule."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = {}
+    for tag, env in (("on", {}), ("off", {"RNVP_WGRAD_STREAM": "0", "RNVP_PDL": "0"})):
+        path = str(tmp_path / f"g_{tag}.pt")
+        code = (f"import sys; sys.path[:0] = [{here!r}]; import conftest; import test_gpu_flow as T; T._grad_dump({path!r})")
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                             timeout=600)
+        assert out.returncode == 0, out.stderr[-3000:]
+        res[tag] = torch.load(path)
+    def gdiff(a, b):
+        num = den = 0.0
+        for k, g in b.items():
+            num += float(((a[k] - g).double() ** 2).sum())
+            den += float((g.double() ** 2).sum())
+        return (num / den) ** 0.5
+
+    # noise floor: the serialised schedule against itself (fp32 atomics reorder sums from run to run and the
+    # stack amplifies that, SURVEY.md 4); a write-after-read or missing-wait bug would be an O(1) error
+    noise = gdiff(res["off"][0], res["off"][1])
+    for rep in (0, 1):
+        assert rel(res["on"][f"ll{rep}"], res["off"][f"ll{rep}"]) < 1e-6
+        d = gdiff(res["on"][rep], res["off"][rep])
+        assert d < 4 * noise + 1e-4, (rep, d, noise)
+    assert gdiff(res["on"][0], res["on"][1]) < 4 * noise + 1e-4

@@ -790,16 +790,16 @@ __global__ void cpl_bwd_a_kernel(const float* __restrict__ dy, const float* __re
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * g.cio; i += blockDim.x)
     if (i % g.cio >= c0 && i % g.cio < c1) atomicAdd(&sums2[i], (double)acc[i]);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-    // K = sum over pixels of dll_b * keep: keep covers half of the positions of a checkerboard
-    // coupling (S*S is even whenever a mask is used) and all positions of a channelwise one
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32) {
+    // K = sum over pixels of dll_b * keep.  keep = 1 - mask covers every position of a channelwise coupling;
+    // of a checkerboard one it covers the positions with (cfg + i + j) even: ceil(S*S/2) of them for cfg 0,
+    // floor(S*S/2) for cfg 1 (closed form: a serial count over S*S positions cost 100 us at S = 64)
     double k = 0.0;
-    for (int b = 0; b < g.B; ++b) k += (double)dll[b];
-    double npos = g.ckbd ? 0.0 : (double)g.S * g.S;
-    if (g.ckbd) {
-      for (int p = 0; p < g.S * g.S; ++p) npos += 1.0 - (double)g.mask_in(p);
-    }
-    atomicAdd(&sums2[2 * g.cio], k * npos);
+    for (int b = threadIdx.x; b < g.B; b += 32) k += (double)dll[b];
+    k = warp_sum_d(k);
+    const int ss = g.S * g.S;
+    const double npos = !g.ckbd ? (double)ss : (double)(g.cfg ? ss / 2 : (ss + 1) / 2);
+    if (threadIdx.x == 0) atomicAdd(&sums2[2 * g.cio], k * npos);
   }
 }
 int k_cpl_bwd_a(const float* dy, const float* xprime, CplGeom g, const float* save, const float* dll,
@@ -834,31 +834,49 @@ __global__ void cpl_bwd_b_kernel(const float* __restrict__ dy, const float* __re
   cpl_chan_range(g.cio, c0, c1);
   int P = g.P(), hw = g.S * g.S;
   float a_scale = 0.f, a_shift = 0.f;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
-    float keep = 1.f - (g.ckbd ? g.mask_in(p) : 0.f);
-    float dl_b = dll[p / hw];
-    float* drow = dst + (int64_t)p * g.cst_pad;
-    for (int c = c0; c < c1; ++c) {
-      float mean = save[c], rstd = save[g.cio + c];
-      float dyv = dy[(int64_t)p * g.C + g.on_off + c];
-      float xp = xprime[(int64_t)p * g.cio + c];
-      float xh = (xp - mean) * rstd;
-      float gv = dyv * keep;
-      float dxp = rstd * (gv - s_m1[c] - xh * s_m2[c]) - kn * rstd * xh + dyv * (1.f - keep);
-      float l = stt[(int64_t)p * g.cst_pad + g.cio + c];
-      float th = tanhf(l);
-      float s = (scale * th + sshift) * keep;
-      float es = expf(s);
-      float xv = x[(int64_t)p * g.C + g.on_off + c];
-      float ds = (dxp * xv * es + dl_b) * keep;
-      drow[c] = maybe_round(dxp * keep, rnd);
-      drow[g.cio + c] = maybe_round(ds * scale * (1.f - th * th), rnd);
-      dxdir[(int64_t)p * g.cio + c] = dxp * es;
-      a_scale += ds * th;
-      a_shift += ds;
+  // Few channels (one channel block, 32-float dst rows): a thread owns a pixel = a 128-byte dst row, which it
+  // would write with 32 scattered 4-byte stores; the rows of the block's 256 pixels are staged in shared
+  // memory instead and leave as one contiguous, fully coalesced 32 KB burst.
+  extern __shared__ float stage[];                 // [256][33] when staged
+  const bool staged = gridDim.y == 1 && g.cst_pad == 32;
+  for (int pb = blockIdx.x * blockDim.x; pb < P; pb += gridDim.x * blockDim.x) {
+    const int p = pb + threadIdx.x;
+    if (p < P) {
+      float keep = 1.f - (g.ckbd ? g.mask_in(p) : 0.f);
+      float dl_b = dll[p / hw];
+      float* drow = staged ? stage + threadIdx.x * 33 : dst + (int64_t)p * g.cst_pad;
+      for (int c = c0; c < c1; ++c) {
+        float mean = save[c], rstd = save[g.cio + c];
+        float dyv = dy[(int64_t)p * g.C + g.on_off + c];
+        float xp = xprime[(int64_t)p * g.cio + c];
+        float xh = (xp - mean) * rstd;
+        float gv = dyv * keep;
+        float dxp = rstd * (gv - s_m1[c] - xh * s_m2[c]) - kn * rstd * xh + dyv * (1.f - keep);
+        float l = stt[(int64_t)p * g.cst_pad + g.cio + c];
+        float th = tanhf(l);
+        float s = (scale * th + sshift) * keep;
+        float es = expf(s);
+        float xv = x[(int64_t)p * g.C + g.on_off + c];
+        float ds = (dxp * xv * es + dl_b) * keep;
+        drow[c] = maybe_round(dxp * keep, rnd);
+        drow[g.cio + c] = maybe_round(ds * scale * (1.f - th * th), rnd);
+        dxdir[(int64_t)p * g.cio + c] = dxp * es;
+        a_scale += ds * th;
+        a_shift += ds;
+      }
+      if (blockIdx.y == 0)
+        for (int c = 2 * g.cio; c < g.cst_pad; ++c) drow[c] = 0.f;
     }
-    if (blockIdx.y == 0)
-      for (int c = 2 * g.cio; c < g.cst_pad; ++c) drow[c] = 0.f;
+    if (staged) {
+      __syncthreads();
+      const int rows = min((int)blockDim.x, P - pb);
+      float4* out = reinterpret_cast<float4*>(dst + (int64_t)pb * 32);
+      for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
+        const float* r = stage + (i >> 3) * 33 + (i & 7) * 4;
+        out[i] = make_float4(r[0], r[1], r[2], r[3]);
+      }
+      __syncthreads();
+    }
   }
   a_scale = warp_sum(a_scale);
   a_shift = warp_sum(a_shift);
@@ -877,7 +895,7 @@ int k_cpl_bwd_b(const float* dy, const float* xprime, const float* x, const floa
                 const float* sshift, float* dst, float* dxdir, float* dscale, float* dsshift, int tf32_round,
                 cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
-  RNVP_CUDA(launch_pdl(cpl_bwd_b_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), 0, st, dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift, tf32_round));
+  RNVP_CUDA(launch_pdl(cpl_bwd_b_kernel, cpl_grid(g.P(), kThreads, g.cio), dim3(kThreads), kThreads * 33 * sizeof(float), st, dy, xprime, x, stt, g, save, sums2, count, dll, scale, sshift, dst, dxdir, dscale, dsshift, tf32_round));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

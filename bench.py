@@ -398,6 +398,8 @@ def run_b200(args):
                                       "RealNVP 64x64x3 inverse sampling (BASELINE configs[3])",
                           "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
                           "parallelism": f"dp{world}" if world > 1 else "single",
+                          **({"bn_stat_exchange": model.stat_exchange, "grad_allreduce": "nccl, bucketed, overlapped"}
+                             if world > 1 else {}),
                           "l2": "per-step working set (activations ~16 GB at B=256) exceeds the 126 MB L2",
                           "optimizer": ("rnvp_optim.Adam (one fused launch, clears the gradients)"
                                         if args.optimizer == "fused" else "torch.optim.Adam(fused=True)") +

@@ -73,7 +73,66 @@ namespace rnvp {
 DpState* plan_dp(rnvp_plan* p);              // runtime.cu (the plan struct is private to it)
 int plan_num_couplings(const rnvp_plan* p);
 
+// ---------------------------------------------------------------------------------------------------------
+// One-shot all-reduce of a small double vector over NVLink peer memory.
+//
+// The 840+ batch-norm statistic exchanges of a step are 48 B ... 8 KB each and strictly serialised by data
+// dependence, so their cost is pure latency.  Instead of an NCCL call (a kernel launch plus its internal
+// handshakes) each exchange is ONE single-CTA kernel: push the local partial sums straight into every
+// rank's inbox (remote stores through the NVSwitch), publish a sequence number with a system-scope release
+// store, wait until every peer's sequence number has arrived in the own inbox, and add the world's vectors up
+// in rank order (so all ranks obtain bit-identical sums).  Inbox slots alternate with the parity of the
+// sequence number: a rank can only be one exchange ahead of the slowest one, because finishing exchange k+1
+// needs every peer's flag k+1, which a peer publishes only after it has finished reading exchange k.
+// A peer that never arrives trips a ~2 s timeout and is counted in `err` instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kXchgThreads = 256;
+__device__ __forceinline__ size_t xchg_flag_off(int world, int cap) { return (size_t)world * 2 * cap * sizeof(double); }
+
+__global__ void __launch_bounds__(kXchgThreads) stats_exchange_kernel(void* const* __restrict__ peers, int rank, int world,
+                                                                      int cap, double* __restrict__ buf, int n,
+                                                                      unsigned long long seq, int* err) {
+  const int slot = (int)(seq & 1ull);
+  // 1. push: my vector into slot [rank][slot] of every rank's inbox (my own included)
+  for (int p = 0; p < world; ++p) {
+    double* dst = reinterpret_cast<double*>(peers[p]) + ((size_t)rank * 2 + slot) * cap;
+    for (int i = threadIdx.x; i < n; i += kXchgThreads) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. publish, 3. wait for everybody
+  if (threadIdx.x < world) {
+    const int p = threadIdx.x;
+    unsigned long long* pflag = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers[p]) + xchg_flag_off(world, cap)) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pflag), "l"(seq) : "memory");
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(peers[rank]) + xchg_flag_off(world, cap)) + p;
+    const long long t0 = clock64();
+    unsigned long long v = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= seq) break;
+      if (clock64() - t0 > 4000000000ll) { atomicAdd(err, 1); break; }      // ~2 s at 2 GHz: a peer is gone
+    }
+  }
+  __syncthreads();
+  // 4. reduce in rank order
+  const double* inbox = reinterpret_cast<const double*>(peers[rank]);
+  for (int i = threadIdx.x; i < n; i += kXchgThreads) {
+    double s = 0.0;
+    for (int p = 0; p < world; ++p) s += inbox[((size_t)p * 2 + slot) * cap + i];
+    buf[i] = s;
+  }
+}
+
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st) {
+  if (dp->xchg_ready && (int)n <= dp->xchg_cap) {
+    const unsigned long long seq = ++dp->xchg_seq;
+    stats_exchange_kernel<<<1, kXchgThreads, 0, st>>>(dp->xchg_peers_dev, dp->rank, dp->world, dp->xchg_cap, buf, (int)n,
+                                                      seq, dp->xchg_err);
+    RNVP_LAUNCH_CHECK();
+    return RNVP_OK;
+  }
   RNVP_REQUIRE(dp->comm != nullptr, "data-parallel communicator not initialised");
   RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, ncclSum_, (ncclComm_t)dp->comm, st));
   return RNVP_OK;
@@ -140,6 +199,58 @@ int rnvp_dp_init(rnvp_plan* plan, const void* id128, int rank, int world) {
   return RNVP_OK;
 }
 
+// ---- NVLink statistic exchange: rank-local inbox, CUDA-IPC handles, peer mappings ------------------------
+int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64) {
+  RNVP_REQUIRE(plan && ipc_handle64 && cap_doubles > 0, "rnvp_dp_xchg_alloc: bad arguments");
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  RNVP_REQUIRE(dp->world > 1 && dp->world <= 16, "statistic exchange: world size %d unsupported (2..16)", dp->world);
+  RNVP_REQUIRE(dp->xchg_local == nullptr, "statistic exchange already allocated");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  const size_t bytes = (size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)dp->world * sizeof(unsigned long long);
+  RNVP_CUDA(cudaMalloc(&dp->xchg_local, bytes));
+  RNVP_CUDA(cudaMemset(dp->xchg_local, 0, bytes));
+  RNVP_CUDA(cudaMalloc(&dp->xchg_err, sizeof(int)));
+  RNVP_CUDA(cudaMemset(dp->xchg_err, 0, sizeof(int)));
+  RNVP_CUDA(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  RNVP_CUDA(cudaIpcGetMemHandle(&h, dp->xchg_local));
+  memcpy(ipc_handle64, &h, sizeof(h));
+  dp->xchg_cap = cap_doubles;
+  return RNVP_OK;
+}
+
+int rnvp_dp_xchg_open(rnvp_plan* plan, const void* all_handles) {
+  RNVP_REQUIRE(plan && all_handles, "rnvp_dp_xchg_open: bad arguments");
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  RNVP_REQUIRE(dp->xchg_local != nullptr, "call rnvp_dp_xchg_alloc first");
+  void* bases[16] = {};
+  for (int r = 0; r < dp->world; ++r) {
+    if (r == dp->rank) { bases[r] = dp->xchg_local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)all_handles + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    RNVP_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    dp->xchg_peer_host[r] = p;
+    bases[r] = p;
+  }
+  RNVP_CUDA(cudaMalloc(&dp->xchg_peers_dev, 16 * sizeof(void*)));
+  RNVP_CUDA(cudaMemcpy(dp->xchg_peers_dev, bases, 16 * sizeof(void*), cudaMemcpyHostToDevice));
+  dp->xchg_seq = 0;
+  dp->xchg_ready = true;
+  return RNVP_OK;
+}
+
+// exchanges that gave up waiting for a peer since the last call (0 in a healthy run); -1 when not in use
+int rnvp_dp_xchg_errors(rnvp_plan* plan) {
+  if (!plan) return -1;
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  if (!dp->xchg_ready) return -1;
+  int e = 0;
+  if (cudaMemcpy(&e, dp->xchg_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  cudaMemset(dp->xchg_err, 0, sizeof(int));
+  return e;
+}
+
 int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets_host, int64_t bucket_elems) {
   RNVP_REQUIRE(plan && flat && offsets_host, "null argument");
   rnvp::DpState* dp = rnvp::plan_dp(plan);
@@ -166,12 +277,30 @@ int rnvp_dp_finalize(rnvp_plan* plan) {
     cudaEventDestroy(dp->ev_comm);
     dp->comm_stream = nullptr;
   }
+  if (dp->xchg_local) {
+    cudaDeviceSynchronize();
+    dp->xchg_ready = false;
+    for (int r = 0; r < 16; ++r)
+      if (dp->xchg_peer_host[r]) { cudaIpcCloseMemHandle(dp->xchg_peer_host[r]); dp->xchg_peer_host[r] = nullptr; }
+    if (dp->xchg_peers_dev) cudaFree(dp->xchg_peers_dev);
+    cudaFree(dp->xchg_local);
+    cudaFree(dp->xchg_err);
+    dp->xchg_peers_dev = nullptr; dp->xchg_local = nullptr; dp->xchg_err = nullptr;
+  }
   delete[] dp->off;
   dp->off = nullptr;
   dp->flat = nullptr;
   dp->rank = 0;
   dp->world = 1;
   return RNVP_OK;
+}
+
+// the reduction the batch-norm statistics go through (NVLink exchange when open and n fits, else NCCL)
+int rnvp_dp_allreduce_stats(rnvp_plan* plan, double* buf, size_t n, void* stream) {
+  RNVP_REQUIRE(plan && buf, "null argument");
+  rnvp::DpState* dp = rnvp::plan_dp(plan);
+  if (dp->world <= 1 || n == 0) return RNVP_OK;
+  return rnvp::dp_allreduce_doubles(dp, buf, n, (cudaStream_t)stream);
 }
 
 int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream) {

@@ -119,6 +119,15 @@ struct DpState {
   int64_t pending_end = -1;          // end of the not-yet-reduced contiguous range
   int64_t bucket_elems = 1 << 20;    // reduce when at least this many elements are pending
   bool launched = false;
+  // one-shot NVLink exchange of the small batch-norm statistic vectors (dp.cu): every rank owns an inbox
+  // [world][2 slots][cap] doubles + [world] flags in device memory that its peers map through CUDA IPC
+  void* xchg_local = nullptr;        // this rank's inbox
+  void** xchg_peers_dev = nullptr;   // device array: inbox base of every rank (own entry = xchg_local)
+  void* xchg_peer_host[16] = {};     // opened peer mappings (to close them)
+  int xchg_cap = 0;                  // doubles per slot
+  unsigned long long xchg_seq = 0;   // exchanges issued so far (all ranks call in the same order)
+  int* xchg_err = nullptr;           // device: number of exchanges that timed out waiting for a peer
+  bool xchg_ready = false;
 };
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st);
 // called after the backward of coupling `ci` was enqueued on `main` (couplings finish last -> first)

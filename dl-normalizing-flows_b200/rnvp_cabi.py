@@ -69,6 +69,10 @@ def _load():
         "rnvp_dp_unique_id": (i32, [vp]),
         "rnvp_dp_init": (i32, [vp, vp, i32, i32]),
         "rnvp_dp_set_grad_layout": (i32, [vp, vp, C.POINTER(C.c_int64), C.c_int64]),
+        "rnvp_dp_xchg_alloc": (i32, [vp, i32, vp]),
+        "rnvp_dp_xchg_open": (i32, [vp, vp]),
+        "rnvp_dp_xchg_errors": (i32, [vp]),
+        "rnvp_dp_allreduce_stats": (i32, [vp, vp, sz, vp]),
         "rnvp_dp_finalize": (i32, [vp]),
         "rnvp_dp_allreduce": (i32, [vp, vp, sz, vp]),
         "rnvp_adam_create": (i32, [C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32, C.POINTER(vp)]),

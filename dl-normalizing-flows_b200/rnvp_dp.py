@@ -90,9 +90,37 @@ class DataParallel(nn.Module):
         uid = exchange_unique_id(make_id, group, device=dev)
         raw = (C.c_ubyte * 128).from_buffer_copy(uid)
         check(lib.rnvp_dp_init(eng.handle, raw, self.rank, self.world))
+        self.stat_exchange = self._open_stat_exchange(eng, dev)
         self._install_layout(eng, bucket_elems)
         eng.dp = self
         self._bucket_elems = bucket_elems
+
+    def _open_stat_exchange(self, eng, dev) -> str:
+        """Map every rank's statistic inbox into every other rank (CUDA IPC over NVLink) so that the 840+
+        batch-norm statistic reductions of a step are one-shot peer-memory kernels instead of NCCL calls.
+        Falls back to NCCL (returns "nccl") when IPC is unavailable or RNVP_DP_XCHG=0; all ranks agree."""
+        import os
+        from rnvp_cabi import lib
+        ok = 1 if (self.world > 1 and self.world <= 16 and os.environ.get("RNVP_DP_XCHG", "1") != "0") else 0
+        handle = (C.c_ubyte * 64)()
+        if ok and lib.rnvp_dp_xchg_alloc(eng.handle, 2 * 1024 + 8, handle) != 0:
+            ok = 0
+        mine = torch.tensor(list(bytes(handle)) + [ok], dtype=torch.uint8, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=self.group)
+        every = [bytes(t.cpu().numpy().tobytes()) for t in every]
+        if not all(e[64] for e in every):
+            return "nccl"
+        blob = b"".join(e[:64] for e in every)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        opened = 1 if lib.rnvp_dp_xchg_open(eng.handle, buf) == 0 else 0
+        # the exchange is collective: use it only if every rank mapped every inbox
+        flag = torch.tensor([opened], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) != 1:
+            raise RuntimeError("statistic exchange: a rank could not map its peers' inboxes (CUDA IPC); "
+                               "set RNVP_DP_XCHG=0 to use NCCL for the batch-norm statistics")
+        return "nvlink"
 
     def _install_layout(self, eng, bucket_elems):
         from rnvp_cabi import check, lib

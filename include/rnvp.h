@@ -206,6 +206,17 @@ int rnvp_dp_init(rnvp_plan* plan, const void* id128_host, int rank, int world);
  * range of coupling i (num_couplings + 1 entries).  Buckets are whole couplings, at least
  * bucket_elems elements (0 = default 1 Mi).                                                  */
 int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets_host, int64_t bucket_elems);
+/* One-shot NVLink exchange for the batch-norm statistic vectors (optional; without it they go through
+ * ncclAllReduce).  Every rank allocates an inbox of `cap_doubles` per (peer, slot) and returns its 64-byte
+ * CUDA-IPC handle; after an all-gather of the handles (rank order, world * 64 bytes) rnvp_dp_xchg_open maps
+ * the peers' inboxes.  From then on every statistic vector of at most `cap_doubles` is reduced by one
+ * single-CTA kernel that pushes it into all inboxes and adds the arrivals up in rank order.
+ * rnvp_dp_xchg_errors returns (and clears) the number of exchanges that timed out waiting for a peer.   */
+int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64_host);
+int rnvp_dp_xchg_open(rnvp_plan* plan, const void* all_handles_host);
+int rnvp_dp_xchg_errors(rnvp_plan* plan);
+/* sum-all-reduce `n` doubles in place on `stream` exactly as the batch-norm statistics are (test hook)  */
+int rnvp_dp_allreduce_stats(rnvp_plan* plan, double* buf, size_t n, void* stream);
 int rnvp_dp_finalize(rnvp_plan* plan);
 /* sum-all-reduce `n` floats in place on `stream` (gradient buckets)         */
 int rnvp_dp_allreduce(rnvp_plan* plan, float* buf, size_t n, void* stream);

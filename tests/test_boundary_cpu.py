@@ -126,6 +126,23 @@ def test_no_cpu_fallback(pkg):
             pkg.logit_transform(x)
 
 
+def test_fused_adam_host_side(pkg):
+    """rnvp_optim.Adam is a torch Optimizer with torch.optim.Adam's group layout; on a CPU model its step
+    raises instead of falling back."""
+    m = _model(pkg)
+    opt = pkg.rnvp_optim.Adam(m, lr=5e-4, weight_decay=5e-5)
+    ref = torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=5e-5)
+    g, r = opt.param_groups[0], ref.param_groups[0]
+    assert len(g["params"]) == len(r["params"]) == len(list(m.parameters()))
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize"):
+        assert g[k] == r[k], k
+    assert opt.state_dict()["param_groups"][0]["params"] == ref.state_dict()["param_groups"][0]["params"]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        opt.step()
+    with pytest.raises(TypeError):
+        pkg.rnvp_optim.Adam(torch.nn.Linear(2, 2))
+
+
 def test_unsupported_hps_raise(pkg):
     prior = torch.distributions.Normal(torch.tensor(0.), torch.tensor(1.))
     with pytest.raises(NotImplementedError):

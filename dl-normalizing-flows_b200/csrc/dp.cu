@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(kXchgThreads) stats_exchange_kernel(void* cons
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st) {
   if (dp->xchg_ready && (int)n <= dp->xchg_cap) {
     const unsigned long long seq = ++dp->xchg_seq;
+    // plain launch: programmatic dependent launch bought nothing here (measured) and the exchange is the one
+    // kernel whose early start could only add waiting peers
     stats_exchange_kernel<<<1, kXchgThreads, 0, st>>>(dp->xchg_peers_dev, dp->rank, dp->world, dp->xchg_cap, buf, (int)n,
                                                       seq, dp->xchg_err);
     RNVP_LAUNCH_CHECK();

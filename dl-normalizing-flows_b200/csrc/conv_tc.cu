@@ -112,6 +112,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (warp-uniform result register on every lane: 1 on the elected lane)
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -374,7 +385,8 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && prm.halo) {
+    if (prm.halo) {
+      if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
       int ai = 0, bi = 0, ti = 0;
       if (prm.halo == 2 && (int)blockIdx.x < num_tiles) {
@@ -413,27 +425,42 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
         }
         umma_commit(&acc_full[as_acc]);
       }
-    } else if (lane == 0) {
+      }
+    } else {
+      // The whole warp walks the loop in lock step and one elected lane issues: descriptors and barrier
+      // addresses are then warp-uniform values (uniform registers), and the per-MMA work of the issuing
+      // thread shrinks to "descriptor + 2 -> tcgen05.mma".  Computed inside an `if (lane == 0)` region every
+      // MMA cost ~16 instructions of descriptor arithmetic and uniform-register election, ~100 cycles -- more
+      // than the tensor pipe needs for an N <= 128 tile, i.e. the issue thread was the bound.
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-      int it_glob = 0, ti = 0;
+      const uint32_t leader = elect_one();
+      const uint64_t a_desc0 = make_desc(smem_u32(smem), 16, 1024);
+      const uint64_t b_desc0 = make_desc(smem_u32(smem) + A_TILE_BYTES, 16, 1024);
+      int s = 0, ti = 0;
+      uint32_t phase = 0;
+      uint64_t soff = 0;                                       // (s * STAGE_BYTES) >> 4, added to the address field
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
         const int as = ti & 1;
         mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int it = 0; it < iters; ++it, ++it_glob) {
-          const int s = it_glob % STAGES;
-          mbar_wait(&full_bar[s], (it_glob / STAGES) & 1);
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full_bar[s], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-          const uint32_t b_addr = a_addr + A_TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)             // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
-            umma_tf32(d_tmem, make_desc(a_addr + k * 32, 16, 1024), make_desc(b_addr + k * 32, 16, 1024), idesc,
-                      (it | k) != 0);
-          umma_commit(&empty_bar[s]);             // frees the smem stage when these MMAs retire
+          const uint64_t ad = a_desc0 + soff, bd = b_desc0 + soff;
+          if (leader) {
+            umma_tf32(d_tmem, ad, bd, idesc, it != 0);          // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
+            umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1);
+            umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1);
+            umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1);
+            umma_commit(&empty_bar[s]);                         // frees the smem stage when these MMAs retire
+          }
+          __syncwarp();
+          soff += STAGE_BYTES >> 4;
+          if (++s == STAGES) { s = 0; soff = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);               // accumulator of this tile complete
+        if (leader) umma_commit(&acc_full[as]);                // accumulator of this tile complete
+        __syncwarp();
       }
     }
   } else {
@@ -985,29 +1012,45 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       }
     } else if (warp == 1) {
       // ===================== MMA issuer =====================
-      if (lane == 0) {
+      // whole warp in lock step, one elected lane issues, descriptors are warp-uniform values that only change
+      // by an address increment per MMA (see the forward kernel: the issue thread was the bound)
+      {
         const uint32_t idesc = make_idesc_tf32(128, N, 1, 1);
-        int ai = 0;
+        const uint32_t leader = elect_one();
+        const uint64_t a_desc0 = make_desc(smem_u32(a_ring), (uint32_t)prm.a_lbo, 512, kLayoutSw128Base32);
+        const uint64_t b_desc0 = make_desc(smem_u32(b_ring), WG_BOX_BYTES, 512, kLayoutSw128Base32);
+        const uint64_t a_step = (uint64_t)(WG_A_STAGE_BYTES >> 4), b_step = (uint64_t)(WG_B_STAGE_BYTES >> 4);
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
+        uint64_t aoff = 0, boff = 0;
         for (int t = t_begin; t < t_end; ++t) {
-          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
-          mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+          mbar_wait(&b_full[bs], bph);
           tc_fence_after();
-          const uint32_t b_addr = smem_u32(b_ring + bs * WG_B_STAGE_BYTES);
+          const uint64_t bd = b_desc0 + boff;
           const uint32_t acc = (t != t_begin);
-          for (int mg = 0; mg < groups; ++mg, ++ai) {
-            const int as = ai % WG_A_STAGES;
-            mbar_wait(&a_full[as], (ai / WG_A_STAGES) & 1);
+          for (int mg = 0; mg < groups; ++mg) {
+            mbar_wait(&a_full[as], aph);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(a_ring + as * WG_A_STAGE_BYTES);
+            const uint64_t ad = a_desc0 + aoff;
+            const uint32_t d = tmem_base + (uint32_t)(mg * N);
+            if (leader) {
+              // 8 x (K = 8 pixels = two 512-byte swizzle atoms = 1024 bytes -> +64 in the address field)
+              umma_tf32(d, ad, bd, idesc, acc);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)       // 8 x (K = 8 pixels = two 512-byte swizzle atoms)
-              umma_tf32(tmem_base + (uint32_t)(mg * N), make_desc(a_addr + ks * 1024, (uint32_t)prm.a_lbo, 512, kLayoutSw128Base32),
-                        make_desc(b_addr + ks * 1024, WG_BOX_BYTES, 512, kLayoutSw128Base32), idesc, acc | (ks != 0));
-            umma_commit(&a_empty[as]);
+              for (int ks = 1; ks < 8; ++ks) umma_tf32(d, ad + 64 * ks, bd + 64 * ks, idesc, 1);
+              umma_commit(&a_empty[as]);
+            }
+            __syncwarp();
+            aoff += a_step;
+            if (++as == WG_A_STAGES) { as = 0; aoff = 0; aph ^= 1; }
           }
-          umma_commit(&b_empty[bs]);
+          if (leader) umma_commit(&b_empty[bs]);
+          __syncwarp();
+          boff += b_step;
+          if (++bs == WG_B_STAGES) { bs = 0; boff = 0; bph ^= 1; }
         }
-        umma_commit(&acc_bar);
+        if (leader) umma_commit(&acc_bar);
+        __syncwarp();
       }
     } else {
       // ===================== epilogue: TMEM -> coalesced fp32 atomics =====================

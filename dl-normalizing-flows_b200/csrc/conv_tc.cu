@@ -386,45 +386,60 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (prm.halo) {
-      if (lane == 0) {
+      // halo mode, same issue discipline as below: converged warp, one elected lane, incremental descriptors.
+      // With resident weights (mode 2) a chunk is ONE barrier wait followed by 36 back-to-back MMAs.
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-      int ai = 0, bi = 0, ti = 0;
+      const uint32_t leader = elect_one();
+      const uint64_t a_desc0 = make_desc(smem_u32(smem), 16, HALO_W * 128);
+      const uint64_t b_desc0 = make_desc(smem_u32(b_ring), 16, 1024);
       if (prm.halo == 2 && (int)blockIdx.x < num_tiles) {
         mbar_wait(&bres_bar, 0);
         tc_fence_after();
       }
+      int as = 0, bs = 0, ti = 0;
+      uint32_t aph = 0, bph = 0;
+      uint64_t aoff = 0, boff = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
         const int as_acc = ti & 1;
         mbar_wait(&acc_empty[as_acc], ((ti >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as_acc * BN);
-        for (int kc = 0; kc < prm.kchunks; ++kc, ++ai) {
-          const int as = ai % prm.a_stages;
-          mbar_wait(&a_full[as], (ai / prm.a_stages) & 1);
+        for (int kc = 0; kc < prm.kchunks; ++kc) {
+          mbar_wait(&a_full[as], aph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + as * HALO_TILE_BYTES);
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
-            // window of tap (dy,dx) = (tap/3-1, tap%3-1): shifted by (dy+1) halo rows and (dx+1) pixels
-            const uint32_t a_tap = a_addr + (uint32_t)(((tap / 3) * HALO_W + tap % 3) * 128);
-            uint32_t b_addr;
-            const int s = bi % STAGES;
-            if (prm.halo == 2) {
-              b_addr = smem_u32(b_ring + (kc * 9 + tap) * B_TILE_BYTES);
-            } else {
-              mbar_wait(&full_bar[s], (bi / STAGES) & 1);
-              tc_fence_after();
-              b_addr = smem_u32(b_ring + s * B_TILE_BYTES);
-            }
+          const uint64_t ad = a_desc0 + aoff;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_tf32(d_tmem, make_desc(a_tap + k * 32, 16, HALO_W * 128), make_desc(b_addr + k * 32, 16, 1024), idesc,
-                        (kc | tap | k) != 0);
-            if (prm.halo != 2) umma_commit(&empty_bar[s]);   // weight tile free once these MMAs retire
+          for (int tap = 0; tap < 9; ++tap) {
+            // window of tap (dy,dx) = (tap/3-1, tap%3-1): shifted by (dy+1) halo rows and (dx+1) pixels of 128 bytes
+            const uint64_t at = ad + (uint64_t)(((tap / 3) * HALO_W + tap % 3) * 8);
+            uint64_t bd;
+            if (prm.halo == 2) {
+              bd = b_desc0 + (uint64_t)((kc * 9 + tap) * (B_TILE_BYTES >> 4));
+            } else {
+              mbar_wait(&full_bar[bs], bph);
+              tc_fence_after();
+              bd = b_desc0 + boff;
+            }
+            if (leader) {
+              umma_tf32(d_tmem, at, bd, idesc, (kc | tap) != 0);
+              umma_tf32(d_tmem, at + 2, bd + 2, idesc, 1);
+              umma_tf32(d_tmem, at + 4, bd + 4, idesc, 1);
+              umma_tf32(d_tmem, at + 6, bd + 6, idesc, 1);
+              if (prm.halo != 2) umma_commit(&empty_bar[bs]);   // weight tile free once these MMAs retire
+            }
+            if (prm.halo != 2) {
+              __syncwarp();
+              boff += B_TILE_BYTES >> 4;
+              if (++bs == STAGES) { bs = 0; boff = 0; bph ^= 1; }
+            }
           }
-          umma_commit(&a_empty[as]);              // halo tile free once all nine taps have read it
+          if (leader) umma_commit(&a_empty[as]);               // halo tile free once all nine taps have read it
+          __syncwarp();
+          aoff += HALO_TILE_BYTES >> 4;
+          if (++as == prm.a_stages) { as = 0; aoff = 0; aph ^= 1; }
         }
-        umma_commit(&acc_full[as_acc]);
-      }
+        if (leader) umma_commit(&acc_full[as_acc]);
+        __syncwarp();
       }
     } else {
       // The whole warp walks the loop in lock step and one elected lane issues: descriptors and barrier
@@ -754,11 +769,13 @@ static int make_patch_map(CUtensorMap* m, const float* base, int B, int S, int n
 }
 
 // Opt-in (RNVP_HALO=1).  The path is correct (tests/test_gpu_ops.py::test_conv_tf32_halo) and cuts the
-// shared-memory feed of a 3x3 conv by 2-3x, but measured on B200 it is NOT faster than nine tap-shifted
-// loads: with <= 128 output channels these convs are bound by the tcgen05.mma issue rate -- an M=128, K=8
-// kind::tf32 instruction occupies the tensor pipe for ~100 cycles however small N is (36 MMAs of N=32 per
-// 128-pixel tile = 1.9 us, exactly the measured 108 us per S=64 launch) -- not by the operand feed.  The
-// resident-weight variant runs one CTA per SM and loses the overlap two CTAs give.  See DESIGN.md 4.
+// shared-memory feed of a 3x3 conv by 2-3x.  Measured on B200 (batch 256, forward): S = 64, 32 channels
+// (resident weights, one barrier wait + 36 back-to-back MMAs per tile) 83 us against 97 us for nine
+// tap-shifted loads; S = 32, 64 channels 79 us against 64 us (two 32-wide n-tiles double the MMA count);
+// S = 16, 128 channels 50 against 52 us.  83 us is the tensor-pipe floor of that layer: an M = 128, K = 8
+// kind::tf32 MMA occupies the pipe for ~65 + 0.5 N cycles (82 at N = 32), so 36 of them per 128-pixel tile
+// take 1.5 us x 55 tiles per SM.  It stays off by default: the gain is 0.4 ms per training step and the
+// resident-weight variant runs one CTA per SM.
 static bool halo_enabled() {
   static int on = -1;
   if (on < 0) {

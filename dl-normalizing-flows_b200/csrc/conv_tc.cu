@@ -363,23 +363,26 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
         }
       }
     } else if (lane == 0) {
+      // ring slot and barrier phase advance incrementally: no division on the issue path
       const int hw = prm.S * prm.S;
-      int it_glob = 0;
+      int s = 0;
+      uint32_t ph = 1;                                   // parity of the "slot free" wait (first pass: free)
       for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x) {
         const int t = prm.rev ? num_tiles - 1 - tt : tt;
         const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
         const int p0 = m_tile * 128;
         const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
-        for (int it = 0; it < iters; ++it, ++it_glob) {
-          const int s = it_glob % STAGES;
-          mbar_wait(&empty_bar[s], ((it_glob / STAGES) & 1) ^ 1);
-          const int tap = it / prm.kchunks, kc = it % prm.kchunks;
+        for (int tap = 0; tap < prm.taps; ++tap) {
           int dy = 0, dx = 0;
           if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          uint8_t* a_dst = smem + s * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-          tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
-          tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+          for (int kc = 0; kc < prm.kchunks; ++kc) {
+            mbar_wait(&empty_bar[s], ph);
+            uint8_t* a_dst = smem + s * STAGE_BYTES;
+            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
+            tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -1001,20 +1004,22 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
     if (warp == 0) {
       // ===================== TMA producer =====================
       if (lane == 0) {
+        // ring slots, barrier phases and the pixel coordinates advance incrementally (no division per tile)
         const int hw = prm.S * prm.S;
-        int ai = 0;
+        int p0 = t_begin * 64;
+        int img0 = p0 / hw, rem = p0 % hw;
+        int as = 0, bs = 0;
+        uint32_t aph = 1, bph = 1;                        // parity of the "slot free" waits (first pass: free)
         for (int t = t_begin; t < t_end; ++t) {
-          const int p0 = t * 64;
-          const int img0 = p0 / hw, row0 = (p0 % hw) / prm.S, col0 = (p0 % hw) % prm.S;
-          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
-          mbar_wait(&b_empty[bs], ((bi / WG_B_STAGES) & 1) ^ 1);
+          const int row0 = rem / prm.S, col0 = rem % prm.S;
+          mbar_wait(&b_empty[bs], bph);
           mbar_expect_tx(&b_full[bs], nbx * WG_BOX_BYTES);
           for (int g = 0; g < nbx; ++g)
             tma_load_4d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &b_full[bs], n0 + 32 * g, col0, row0, img0);
-          for (int mg = 0; mg < groups; ++mg, ++ai) {
-            const int as = ai % WG_A_STAGES;
+          if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1; }
+          for (int mg = 0; mg < groups; ++mg) {
             const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);       // taps in this M-group
-            mbar_wait(&a_empty[as], ((ai / WG_A_STAGES) & 1) ^ 1);
+            mbar_wait(&a_empty[as], aph);
             mbar_expect_tx(&a_full[as], tl_n * kb * WG_BOX_BYTES);
             for (int tl = 0; tl < tl_n; ++tl) {
               const int tap = tap0 + mg * prm.tpm + tl;
@@ -1024,7 +1029,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
                 tma_load_4d(a_ring + as * WG_A_STAGE_BYTES + (tl * kb + j) * WG_BOX_BYTES, &tmX, &a_full[as],
                             k0 + 32 * j, col0 + dx, row0 + dy, img0);
             }
+            if (++as == WG_A_STAGES) { as = 0; aph ^= 1; }
           }
+          rem += 64;
+          while (rem >= hw) { rem -= hw; ++img0; }       // a 64-pixel tile spans several images when S < 8
         }
       }
     } else if (warp == 1) {

@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--mode", default="train", choices=["train", "sample"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true",
+                    help="skip timing the unmodified reference's own PyTorch-eager CUDA path on this GPU "
+                         "(gpu_eager_baseline; 1-GPU runs only, needs oracle/_ref)")
     ap.add_argument("--config", default="A", choices=["A", "c3"],
                     help="A: RealNVP 64x64x3, base 32, 4 blocks, 5 scales (BASELINE configs[1], the judged line); "
                          "c3: the 32x32 two-scale variant, base 64, 8 blocks (BASELINE configs[2], batch 512)")
@@ -90,9 +93,87 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# the reference algorithm on the CPU (oracle port)
+# the reference on the host cores: its own code from oracle/_ref (kind "reference"), else the oracle port
 # ------------------------------------------------------------------------------------------
-def cpu_train_step_factory(batch):
+def _ref_modules(cpu):
+    """(flow_realnvp, utils) of the UNMODIFIED reference (byte-compiled into oracle/_ref by oracle/build_ref.py),
+    or None when it was not built (then the oracle port is timed instead)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_loader
+        if ref_loader.available():
+            f, _m, u = ref_loader.load(cpu=cpu)
+            return f, u
+    except Exception as e:                      # pragma: no cover - diagnostic only
+        print(f"[bench] reference modules unavailable: {e}", file=sys.stderr)
+    return None
+
+
+def ref_train_step_factory(batch, device="cpu"):
+    """train.py:176-200 replayed literally on the reference's own RealNVP: zero_grad, logit_transform on the CPU
+    batch (train.py:187), .to(device), model(x), loss, .item(), backward, Adam step."""
+    import torch
+    cpu = device == "cpu"
+    mods = _ref_modules(cpu)
+    if cpu:
+        torch.set_num_threads(os.cpu_count())
+    if mods is None:
+        if not cpu:
+            return None, None, None
+        return cpu_port_train_step_factory(batch) + ("port",)
+    f, u = mods
+    dev = torch.device(device)
+    torch.manual_seed(0)
+    prior = torch.distributions.Normal(torch.tensor(0., device=dev), torch.tensor(1., device=dev), validate_args=False)
+    hps = u.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True)
+    assert CFG["num_scales"] == 5, "the in-tree reference hard-codes five scales"
+    model = f.RealNVP(CFG["channels"], CFG["image"], prior, hps).to(dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, weight_decay=5e-5)            # train.py:134
+    g = torch.Generator().manual_seed(0)
+    x_img = torch.randint(0, 256, (batch, CFG["channels"], CFG["image"], CFG["image"]), generator=g,
+                          dtype=torch.uint8).float() / 255.0
+
+    def step():
+        opt.zero_grad()
+        x, logdet = u.logit_transform(x_img)
+        x, logdet = x.to(dev), logdet.to(dev)
+        logll, weight_scale = model(x)
+        logll = (logll + logdet).mean()
+        loss = -logll + 5e-5 * weight_scale
+        v = logll.item()
+        loss.backward()
+        opt.step()
+        return v
+    return step, (torch.get_num_threads() if cpu else 0), "reference"
+
+
+def ref_sample_step_factory(batch, device="cpu"):
+    import torch
+    cpu = device == "cpu"
+    mods = _ref_modules(cpu)
+    if cpu:
+        torch.set_num_threads(os.cpu_count())
+    if mods is None:
+        if not cpu:
+            return None, None, None
+        return cpu_port_sample_step_factory(batch) + ("port",)
+    f, u = mods
+    dev = torch.device(device)
+    torch.manual_seed(0)
+    prior = torch.distributions.Normal(torch.tensor(0., device=dev), torch.tensor(1., device=dev), validate_args=False)
+    hps = u.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True)
+    model = f.RealNVP(CFG["channels"], CFG["image"], prior, hps).to(dev)
+    model.eval()
+
+    def step():
+        with torch.no_grad():                                                        # train.py:253-257
+            imgs, _ = u.logit_transform(model.sample(size=batch), reverse=True)
+            return float(imgs.mean())
+    return step, (torch.get_num_threads() if cpu else 0), "reference"
+
+
+def cpu_port_train_step_factory(batch):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import realnvp_oracle as O
@@ -118,7 +199,7 @@ def cpu_train_step_factory(batch):
     return step, torch.get_num_threads()
 
 
-def cpu_sample_step_factory(batch):
+def cpu_port_sample_step_factory(batch):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import realnvp_oracle as O
@@ -153,19 +234,24 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 64 if args.mode == "train" else 64           # BASELINE configs[0]: batch 64 on the CPU
-    factory = cpu_train_step_factory if args.mode == "train" else cpu_sample_step_factory
-    step, threads = factory(batch)
+    batch = 64                                           # BASELINE configs[0]: batch 64 on the CPU
+    factory = ref_train_step_factory if args.mode == "train" else ref_sample_step_factory
+    if args.config != "A":                               # the two-scale variant is not in the reference tree
+        factory = (lambda b: cpu_port_train_step_factory(b) + ("port",)) if args.mode == "train" else \
+                  (lambda b: cpu_port_sample_step_factory(b) + ("port",))
+    step, threads, kind = factory(batch)
     warm = min(args.warmup, 1)
     med, n = time_cpu(step, warm, max(1, min(args.steps, 5)), budget_s=120.0)
     v = batch / med
     unit = "img/s"
+    what = ("the UNMODIFIED reference (byte-compiled into oracle/_ref), train.py:176-200 replayed on its RealNVP"
+            if kind == "reference" else "oracle port of the reference algorithm, torch CPU ops")
     out = {"metric": METRIC if args.mode == "train" else "sample imgs/s RealNVP 64x64x3", "value": v, "unit": unit,
            "n_gpus": args.gpus, "steps": n, "warmup": warm, "ms_per_step": med * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
            "config": {"workload": "RealNVP 64x64x3->4x4x48, 4 res-blocks, base-dim 32 (BASELINE configs[0])",
-                      "batch_per_step": batch, "note": "oracle port of the reference algorithm, torch CPU ops"},
-           "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                      "batch_per_step": batch, "note": what},
+           "cpu_baseline": {"value": v, "unit": unit, "cores": threads, "kind": kind,
                             "sample": f"{n} steps of batch {batch} ({args.mode})"},
            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -175,7 +261,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------
 # the B200 path
 # ------------------------------------------------------------------------------------------
-def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
+def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B, fused_reduce=True):
     """Algorithmic traffic / flops of one profiled launch class (fp32 NHWC, every operand once)."""
     pad = lambda v, m: (v + m - 1) // m * m
     P = B * S * S
@@ -191,13 +277,106 @@ def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B):
         flops = 2.0 * P * cin * cout * taps
     elif kind == 3:             # bn+relu apply: read x, write h
         byt, flops = 4 * 2 * P * cin, 0.0
+    elif fused_reduce:          # bn backward, tensor-core tier: the reduce rides in the dgrad epilogue; only the apply
+        byt, flops = 4 * 3 * P * cin, 0.0          # kernel runs (read g, x; write dx)
     else:                       # bn backward = reduce (read g, x; write g*mask) + apply (read g, x; write dx)
         byt, flops = 4 * 6 * P * cin, 0.0
     return byt, flops
 
 
+def kernel_name_of(kind, taps, cin, cout, math, xform):
+    """The CUDA kernel (as ncu names it) a profiled launch class runs in."""
+    if kind in (0, 1):
+        if math != "tf32":
+            return "conv_fwd_fp32_kernel"
+        bn = 32 if cout <= 32 else (64 if cout <= 64 else 128)
+        return f"conv_fwd_tf32_kernel<{bn},{1 if (kind == 0 and xform) else 0}>"
+    if kind == 2:
+        return "conv_wgrad_tf32_kernel" if math == "tf32" else "conv_wgrad_fp32_kernel"
+    return "bn_relu_kernel" if kind == 3 else "bn_bwd_apply_kernel"
+
+
+def gpu_eager_baseline(args, dev, B):
+    """The UNMODIFIED reference on cuda:0 through its own eager path (cuDNN / ATen), train.py:176-200 replayed at the
+    bench's batch: 3 warm-up + 5 timed steps per setting.  torch's default lets cuDNN use TF32 for convolutions
+    (torch.backends.cudnn.allow_tf32 = True), which is what the reference gets on this GPU; the strict-fp32 setting
+    is timed beside it."""
+    import gc
+    import torch
+    out = {"batch": B, "steps": 5, "warmup": 3, "unit": "img/s", "kind": "reference",
+           "what": "reference RealNVP (oracle/_ref), PyTorch eager on the same GPU, train.py:176-200 incl. CPU logit_transform, "
+                   ".item() and torch.optim.Adam" if args.mode == "train" else "reference model.sample + inverse logit, eager"}
+    for tag, allow in (("cudnn_tf32_default", True), ("fp32_strict", False)):
+        torch.backends.cudnn.allow_tf32 = allow
+        try:
+            factory = ref_train_step_factory if args.mode == "train" else ref_sample_step_factory
+            step, _t, kind = factory(B, device=str(dev))
+            if step is None:
+                return {"unavailable": "oracle/_ref not built"}
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                step()
+            torch.cuda.synchronize()
+            out[tag] = B * 5 / (time.perf_counter() - t0)
+        except Exception as e:                                    # e.g. out of memory at a large batch
+            out[tag] = None
+            out[tag + "_error"] = str(e)[:200]
+        finally:
+            step = None
+            gc.collect()
+            torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32 = True
+    return out
+
+
+def dp_consistency_check(pkg, model, net, dev, rank, world):
+    """Data-parallel result == single process on the concatenated batch (per-sample log-likelihood of this rank's
+    shard and the averaged gradient), at a small batch so that rank 0 can run the global batch alone."""
+    import copy
+    import torch
+    import torch.distributed as dist
+    b = 4
+    g = torch.Generator().manual_seed(77)
+    xs = torch.randn(world * b, CFG["channels"], CFG["image"], CFG["image"], generator=g).to(dev)
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.train()
+    net.zero_grad(set_to_none=True)
+    ll, ws = model(xs[rank * b:(rank + 1) * b].contiguous())
+    (-ll.mean() + 5e-5 * ws).backward()
+    key = next(k for k, p in net.named_parameters() if k.endswith("out_block.2.conv.weight_v"))
+    gdp = dict(net.named_parameters())[key].grad.detach().clone()
+    gathered = [torch.zeros_like(ll) for _ in range(world)]
+    dist.all_gather(gathered, ll.detach())
+    ok, detail = True, {}
+    if rank == 0:
+        prior = torch.distributions.Normal(torch.tensor(0., device=dev), torch.tensor(1., device=dev), validate_args=False)
+        ref = pkg.RealNVP(CFG["channels"], CFG["image"], prior,
+                          pkg.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True),
+                          **({} if CFG["num_scales"] == 5 else {"num_scales": CFG["num_scales"]})).to(dev)
+        ref.load_state_dict(sd)
+        ref.set_math("tf32" if net.engine().math == pkg.rnvp_cabi.MATH_TF32 else "fp32")
+        ref.train()
+        ll1, ws1 = ref(xs)
+        (-ll1.mean() + 5e-5 * ws1).backward()
+        g1 = dict(ref.named_parameters())[key].grad
+        e_ll = float((torch.cat(gathered) - ll1.detach()).abs().max() / ll1.detach().abs().max())
+        e_g = float((gdp - g1).norm() / g1.norm())
+        detail = {"ll_rel": e_ll, "grad_rel_l2": e_g, "global_batch": world * b}
+        ok = e_ll < 1e-4 and e_g < 0.1
+        del ref
+    net.load_state_dict(sd)                        # running statistics back to where they were
+    net.zero_grad(set_to_none=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    return {"status": "ok" if int(flag) else "MISMATCH", **detail}
+
+
 def run_b200(args):
-    os.environ["NCCL_DEBUG"] = os.environ.get("RNVP_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
+    # NCCL_DEBUG is left as the environment has it: stdout is redirected to stderr for the duration of the run
+    # (see main), so NCCL's INFO lines cannot break the one-JSON-line contract and the driver can count ranks
     import torch
     import torch.distributed as dist
     pkg = importlib.import_module("dl-normalizing-flows_b200")
@@ -242,9 +421,12 @@ def run_b200(args):
         opt.step()
         return loss
 
+    sample_out = {}
+
     def sample_step(_):
         with torch.no_grad():
             imgs, _ = pkg.logit_transform(net.sample(B), reverse=True)
+        sample_out["imgs"] = imgs
         return imgs.mean()
 
     net.train(args.mode == "train")
@@ -275,6 +457,11 @@ def run_b200(args):
         note(f"warm-up step {i} enqueued")
     barrier()
     note("warm-up done")
+    dp_check = None
+    if world > 1 and args.mode == "train":
+        dp_check = dp_consistency_check(pkg, model, net, dev, rank, world)
+        opt.zero_grad(set_to_none=args.optimizer == "torch")
+        barrier()
 
     # ---- device-resident timing -------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -298,9 +485,16 @@ def run_b200(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end to end from pinned host memory ----------------------------------------------------------
+    host_imgs = (torch.empty(B, CFG["channels"], CFG["image"], CFG["image"], dtype=torch.float32).pin_memory()
+                 if args.mode == "sample" else None)
+
     def e2e_step():
-        out = step(host_u8.to(dev, non_blocking=True)) if args.mode == "train" else step(None)
-        return float(out)                                     # the caller's logll.item() (train.py:196)
+        if args.mode == "train":
+            return float(step(host_u8.to(dev, non_blocking=True)))    # the caller's logll.item() (train.py:196)
+        step(None)
+        host_imgs.copy_(sample_out["imgs"], non_blocking=True)        # a sampler's result is the images (train.py:257-259)
+        torch.cuda.synchronize()
+        return float(host_imgs[0, 0, 0, 0])
     for _ in range(2):                                        # this path's own warm-up (allocator, pinned-copy queue)
         e2e_step()
     barrier()
@@ -314,7 +508,7 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(te)
     h2d = host_u8.numel() if args.mode == "train" else 0
-    d2h = 4
+    d2h = 4 if args.mode == "train" else host_imgs.numel() * 4
 
     # ---- per-kernel-class event timing: the roofline line ---------------------------------------------
     roof = None
@@ -351,44 +545,80 @@ def run_b200(args):
                 json.dump({"batch": B, "profiled_steps": nprof, "classes": classes}, f, indent=0)
         for r in classes:
             by_kind[names[r["kind"]]] = by_kind.get(names[r["kind"]], 0.0) + r["ms"] / nprof
-        if classes:
-            top = classes[0]
-            if True:
-                byt, fl = conv_alg_bytes_and_flops(top["kind"], top["S"], top["taps"], top["cin"], top["cout"], B)
-                dur = top["ms"] / top["launches"] / 1e3
-                gbs, tfs = byt / dur / 1e9, fl / dur / 1e12
-                # the roof that bounds this launch: bytes/HBM vs flops/tensor (tf32 = half the bf16 rate)
-                t_hbm, t_tc = byt / (peaks["hbm_gbs"] * 1e9), fl / (peaks["bf16_tflops"] * 0.5e12)
-                if t_hbm >= t_tc:
-                    roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": gbs / peaks["hbm_gbs"], "traffic": None}
-                else:
-                    roof = {"bound": "tensor", "achieved": tfs, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                            "frac": tfs / peaks["bf16_tflops"], "traffic": None}
-                roof["kernel"] = (f"{names[top['kind']]}_{args.math} S={top['S']} {int(top['taps'] ** 0.5)}x{int(top['taps'] ** 0.5)} "
-                                  f"{top['cin']}->{top['cout']}" if top["kind"] < 3 else
-                                  f"{names[top['kind']]} S={top['S']} C={top['cin']}")
-                roof["launches_per_step"] = top["launches"] // nprof
-                roof["avg_us"] = dur * 1e6
-                roof["share_of_profiled_kernel_time"] = top["ms"] / tot
-                roof["peak_source"] = peaks["src"]
-                roof["schedule"] = ("durations taken with every kernel on one stream (rnvp_prof_enable switches the "
-                                    "wgrad side stream off), CUDA events around each launch")
-                try:                                          # DRAM bytes per launch from the committed ncu capture
-                    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                        roof["traffic"] = json.load(f).get(roof["kernel"])
-                except Exception:
-                    pass
-                roof["algorithmic_bytes_per_launch"] = byt
-                roof["algorithmic_flops_per_launch"] = fl
+        xform_on = args.math == "tf32" and os.environ.get("RNVP_XFORM", "1") != "0"
+        groups = {}
+        for r in classes:
+            byt, fl = conv_alg_bytes_and_flops(r["kind"], r["S"], r["taps"], r["cin"], r["cout"], B,
+                                               fused_reduce=args.math == "tf32")
+            r["alg_bytes"], r["alg_flops"] = byt, fl
+            r["kernel"] = kernel_name_of(r["kind"], r["taps"], r["cin"], r["cout"], args.math, xform_on)
+            gsum = groups.setdefault(r["kernel"], dict(ms=0.0, launches=0, bytes=0.0, flops=0.0))
+            gsum["ms"] += r["ms"]; gsum["launches"] += r["launches"]
+            gsum["bytes"] += byt * r["launches"]; gsum["flops"] += fl * r["launches"]
+        if groups:
+            # the dominant kernel = the CUDA kernel (ncu name) with the largest share of the profiled kernel time;
+            # achieved = its algorithmic bytes (flops) per launch / its average launch duration, over all its launches
+            kname, gk = max(groups.items(), key=lambda kv: kv[1]["ms"])
+            dur = gk["ms"] / gk["launches"] / 1e3
+            byt, fl = gk["bytes"] / gk["launches"], gk["flops"] / gk["launches"]
+            gbs, tfs = byt / dur / 1e9, fl / dur / 1e12
+            tf32_peak = peaks["bf16_tflops"] * 0.5            # kind::tf32 runs at half the bf16 rate
+            t_hbm, t_tc = byt / (peaks["hbm_gbs"] * 1e9), fl / (tf32_peak * 1e12)
+            if t_hbm >= t_tc:
+                roof = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+            else:
+                roof = {"bound": "tensor", "achieved": tfs, "peak": tf32_peak, "unit": "TFLOP/s",
+                        "frac": tfs / tf32_peak, "traffic": None,
+                        "peak_note": "tf32 tensor peak taken as half the measured sustained bf16 cuBLAS rate"}
+            roof["kernel"] = kname
+            roof["launches_per_step"] = gk["launches"] // nprof
+            roof["avg_us"] = dur * 1e6
+            roof["share_of_profiled_kernel_time"] = gk["ms"] / tot
+            roof["peak_source"] = peaks["src"]
+            roof["schedule"] = ("durations taken with every kernel on one stream (rnvp_prof_enable switches the "
+                                "wgrad side stream off), CUDA events around each launch")
+            roof["algorithmic_bytes_per_launch"] = byt
+            roof["algorithmic_flops_per_launch"] = fl
+            roof["hbm_frac_of_this_kernel"] = gbs / peaks["hbm_gbs"]
+            roof["tensor_frac_of_this_kernel"] = tfs / tf32_peak
+            try:                                          # DRAM bytes per launch from the committed ncu capture
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    roof["traffic"] = json.load(f).get(kname)
+            except Exception:
+                pass
+            roof["by_kernel"] = {k: {"share": v["ms"] / tot, "launches_per_step": v["launches"] // nprof,
+                                     "avg_us": v["ms"] / v["launches"] * 1e3,
+                                     "hbm_frac": v["bytes"] / (v["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                     "tensor_frac": v["flops"] / (v["ms"] / 1e3) / 1e12 / tf32_peak}
+                                 for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+            # whole-step roofline on SURVEY.md 8(d) algorithmic bytes: conv activations in + out once each
+            # (41.436 M elements per image and pass, fp32 storage), training = 2.5 passes
+            if args.config == "A":
+                step_bytes = 41.436e6 * 4 * (2.5 if args.mode == "train" else 1.0) * B
+                roof["step"] = {"algorithmic_bytes_per_step": step_bytes,
+                                "ms_at_hbm_roof": step_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3,
+                                "frac": step_bytes / (peaks["hbm_gbs"] * 1e9) / (ms / args.steps / 1e3),
+                                "tensor_frac": value / world * (3 if args.mode == "train" else 1) * GFLOP_FWD_PER_IMG / 1e3 / tf32_peak}
+
+    # ---- the reference's own PyTorch-eager CUDA path on this GPU ("the bar on the box") ---------
+    eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_eager and args.config == "A":
+        net.engine().release_workspaces()                      # hand the training workspace back before the eager model
+        torch.cuda.empty_cache()
+        eager = gpu_eager_baseline(args, dev, B)
 
     # ---- CPU baseline (bounded sample of the same workload) ---------------------------------------------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        factory = cpu_train_step_factory if args.mode == "train" else cpu_sample_step_factory
-        cstep, threads = factory(64)
+        if args.config == "A":
+            factory = ref_train_step_factory if args.mode == "train" else ref_sample_step_factory
+            cstep, threads, kind = factory(64)
+        else:
+            factory = cpu_port_train_step_factory if args.mode == "train" else cpu_port_sample_step_factory
+            (cstep, threads), kind = factory(64), "port"
         med, n = time_cpu(cstep, 1, 3, budget_s=25.0)
-        cpu = {"value": 64 / med, "unit": "img/s", "cores": threads, "kind": "port",
+        cpu = {"value": 64 / med, "unit": "img/s", "cores": threads, "kind": kind,
                "sample": f"{n} {args.mode} steps of batch 64 (BASELINE configs[0]) on the host cores"}
 
     if rank == 0:
@@ -413,7 +643,8 @@ def run_b200(args):
                "e2e": {"value": e2e_value, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches),
                "achieved_tflops_algorithmic": value * tr_flops / 1e3,
-               "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+               "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager,
+               **({"dp_check": dp_check} if world > 1 else {}),
                "kernel_time_ms_by_kind_per_step": by_kind, "kernel_classes": classes[:16]}
         _RECORD.append(json.dumps(out))
     if world > 1:

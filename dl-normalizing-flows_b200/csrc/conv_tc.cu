@@ -192,28 +192,29 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // registers (BN partial sums taken there), the result is written to swizzled smem and leaves through
 // a TMA store -- every global access of the epilogue is a full-line bulk transfer, and the tensor
 // map clips ragged row / channel counts.
+//
+// XF = 1 ("BN prologue"): the A operand in HBM is the RAW pre-BN activation x; four extra warps rewrite
+// every landed A tile in place to h = tf32(relu(x * scale + shift)) before the MMA warp may read it
+// (TMA -> full barrier -> transform -> fence.proxy.async -> ready barrier -> tcgen05.mma), so
+// BatchNorm2d + ReLU (modules_realnvp.py:83-85, 139-141) cost no pass over the tensor and relu(bn(x))
+// never exists in HBM.  The per-channel coefficients are computed by every CTA in its prologue from the
+// batch sums the producing conv's epilogue accumulated (or from the running statistics in eval mode);
+// CTA 0 also saves (mean, rstd, scale, shift) for the backward pass and updates the running statistics.
+// Out-of-image pixels of a 3x3 tap were zero-filled by TMA and must stay zero (the reference pads the
+// ACTIVATED tensor), so the transform skips them.
 // ---------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 32 fp32
 constexpr int EPI_BOX_BYTES = 32 * 128;  // 32 rows x 32 fp32
-constexpr int EPI_BYTES_PER_WARP = 3 * EPI_BOX_BYTES;   // 1 residual + 2 output staging boxes
 constexpr int TC_MAX_STAGES = 8;
-// 3x3 "halo" mode (S >= 16): a CTA tile is an 8 x 16 pixel patch of one image.  Per 32-channel chunk ONE TMA
-// box of (8+2) x (16+2) pixels lands in shared memory (zero-filled outside the image) and all nine taps read
-// it through descriptors whose start address is shifted by whole 128-byte pixel rows: tcgen05 applies the
-// 128B swizzle to absolute shared-memory address bits (profiles/r01_probe_shifted_descriptor_windows.log),
-// so a row-shifted window of a swizzled TMA tile is a valid operand, with SBO = 10 pixels between the
-// 8-pixel row groups.  The activation tile is fetched once instead of nine times.
-constexpr int HALO_W = 10, HALO_H = 18;
-constexpr int HALO_TILE_BYTES = 23 * 1024;       // 180 rows x 128 B = 23040, rounded to the 1024-byte swizzle period
-constexpr int HALO_MAX_A_STAGES = 4;
+constexpr int XF_MAX_K = 512;            // input channels (padded) the BN prologue keeps coefficients for
 // BN = 128 runs one CTA per SM: it gets eight epilogue warps (two per TMEM lane quarter, each owning half
 // of the column chunks) so that twice as many residual prefetches / result stores are in flight, and a
 // three-deep ring to pay for their staging buffers.  The narrower tiles keep four warps (two CTAs per SM).
-template <int BN> struct TcCfg {
-  static constexpr int STAGES = BN == 32 ? 3 : (BN == 64 ? 2 : 3);
+template <int BN, int XF> struct TcCfg {
+  static constexpr int STAGES = XF ? (BN == 128 ? 4 : 3) : (BN == 32 ? 3 : (BN == 64 ? 2 : 3));
   static constexpr int EPI_WARPS = BN == 128 ? 8 : 4;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int XF_WARPS = XF ? 4 : 0;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
   static constexpr int MIN_CTAS = BN == 128 ? 1 : 2;     // register cap: two CTAs of the narrow tiles per SM
 };
 
@@ -222,54 +223,91 @@ struct ConvTcParams {
   double* stats;
   const float* bn_save;              // non-null: fused ReLU+BN backward epilogue (tmR maps the raw activations)
   int has_res;
+  int round_out;                     // round the result to TF32 (cvt.rna): it is the raw operand of another conv MMA
   int P, n, taps, kchunks;           // kchunks = kpad / 32
-  int S;
+  int S, log2S;
   int m_tiles, n_tiles;
   int stages;                        // depth of the smem ring (<= TC_MAX_STAGES)
+  int out_bufs;                      // output staging boxes per epilogue warp (1 or 2); a residual box precedes them if has_res
   int rev;                           // walk the tiles from the last to the first (L2 reuse, see next_sweep_dir)
-  int halo;                          // 3x3 halo mode: patch tiles, A ring of `a_stages` halo tiles, B ring of `stages`
-  int a_stages;
-  int b_tiles;                       // halo mode: weight tiles held in shared memory (ring depth, or 9 * kchunks resident)
-  int tiles_x, tiles_per_img;        // halo mode: patches per image row / per image
+  // BN prologue (XF kernels)
+  int xf_mode;                       // 1 batch statistics from xf_sums, 0 running statistics, 2 coefficients from xf_save
+  int xf_C;                          // real input channels
+  const double* xf_sums;             // [2C] sum, sum of squares over xf_count values
+  double xf_count;
+  const float* xf_gamma;
+  const float* xf_beta;
+  float* xf_rm;
+  float* xf_rv;
+  float* xf_save;                    // [4C] mean, rstd, scale, shift
 };
 
 // byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
 __device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 
-template <int BN>
-__global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                   const __grid_constant__ CUtensorMap tmB,
-                                                                   const __grid_constant__ CUtensorMap tmY,
-                                                                   const __grid_constant__ CUtensorMap tmR,
-                                                                   const ConvTcParams prm) {
+// BN coefficients of channels [0, kpad) into smem (scale at [c], shift at [kpad_max + c]); channels >= C get 0 / 0.
+// Block `writer` also saves them for the backward pass and updates the running statistics (nn.BatchNorm2d).
+__device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* s_scale, float* s_shift, int kpad, bool writer) {
+  const int C = prm.xf_C;
+  for (int c = threadIdx.x; c < kpad; c += blockDim.x) {
+    float sc = 0.f, sh = 0.f;
+    if (c < C) {
+      if (prm.xf_mode == 2) {
+        sc = prm.xf_save[2 * C + c];
+        sh = prm.xf_save[3 * C + c];
+      } else {
+        const BnCoef k = prm.xf_mode == 1
+                             ? bn_coef_from_sums(prm.xf_sums[c], prm.xf_sums[C + c], prm.xf_count, prm.xf_gamma[c], prm.xf_beta[c])
+                             : bn_coef_from_running(prm.xf_rm[c], prm.xf_rv[c], prm.xf_gamma[c], prm.xf_beta[c]);
+        sc = k.scale;
+        sh = k.shift;
+        if (prm.xf_mode == 1 && writer) {
+          prm.xf_save[c] = k.mean;
+          prm.xf_save[C + c] = k.rstd;
+          prm.xf_save[2 * C + c] = k.scale;
+          prm.xf_save[3 * C + c] = k.shift;
+          const double cnt = prm.xf_count;
+          const double unb = cnt > 1.0 ? (double)k.var * cnt / (cnt - 1.0) : (double)k.var;
+          prm.xf_rm[c] = (1.f - kBnMomentum) * prm.xf_rm[c] + kBnMomentum * k.mean;
+          prm.xf_rv[c] = (1.f - kBnMomentum) * prm.xf_rv[c] + kBnMomentum * (float)unb;
+        }
+      }
+    }
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+  }
+}
+
+template <int BN, int XF>
+__global__ void __launch_bounds__(TcCfg<BN, XF>::THREADS, TcCfg<BN, XF>::MIN_CTAS)
+conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
+                     const ConvTcParams prm) {
   const int STAGES = prm.stages;
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // flat mode: ring of (A tile + B tile) stages.  halo mode: A ring of halo tiles, then a B ring of weight tiles
-  uint8_t* b_ring = smem + prm.a_stages * HALO_TILE_BYTES;
-  uint8_t* epi_smem = prm.halo ? b_ring + prm.b_tiles * B_TILE_BYTES : smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
-  __shared__ __align__(8) uint64_t a_full[HALO_MAX_A_STAGES];
-  __shared__ __align__(8) uint64_t a_empty[HALO_MAX_A_STAGES];
-  __shared__ __align__(8) uint64_t bres_bar;          // halo mode 2: all weight tiles of this CTA's n-tile are resident
+  __shared__ __align__(8) uint64_t ready_bar[XF ? TC_MAX_STAGES : 1];   // XF: A tile transformed
   __shared__ __align__(8) uint64_t acc_full[2];
   __shared__ __align__(8) uint64_t acc_empty[2];
-  constexpr int EW = TcCfg<BN>::EPI_WARPS;
+  constexpr int EW = TcCfg<BN, XF>::EPI_WARPS;
   constexpr int CH_PER_WARP = (BN / 32) / (EW / 4) < 1 ? 1 : (BN / 32) / (EW / 4);   // column chunks per epilogue warp
   __shared__ __align__(8) uint64_t res_bar[EW];
   __shared__ uint32_t tmem_base_slot;
   __shared__ float red_sum[EW][BN];
   __shared__ float red_sq[EW][BN];
-  __shared__ __align__(16) float coef[2 * BN];  // (scale, shift) of the fused BN backward (n_tiles == 1)
+  __shared__ __align__(16) float coef[XF ? 2 * XF_MAX_K : 2 * BN];   // XF: BN-prologue (scale | shift); else the fused
+                                                                      // BN backward's (scale | shift) when n_tiles == 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int iters = prm.taps * prm.kchunks;
   const int num_tiles = prm.m_tiles * prm.n_tiles;
-  const bool bnbwd = prm.bn_save != nullptr;
+  const bool bnbwd = !XF && prm.bn_save != nullptr;
   const bool coef_in_smem = bnbwd && prm.n_tiles == 1;          // else read through L1 from global
 
   if (threadIdx.x == 0) {
@@ -280,12 +318,8 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      if (XF) mbar_init(&ready_bar[s], TcCfg<BN, XF>::XF_WARPS);
     }
-    for (int s = 0; s < HALO_MAX_A_STAGES; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-    }
-    mbar_init(&bres_bar, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], EW);       // one arrive per epilogue warp
@@ -300,11 +334,14 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
   // chain of successors pile up on the SMs holding shared memory and TMEM columns.
   pdl_wait();
   pdl_trigger();
-  if (coef_in_smem)
+  if constexpr (XF) {
+    xf_coefficients(prm, coef, coef + XF_MAX_K, prm.kchunks * 32, blockIdx.x == 0);
+  } else if (coef_in_smem) {
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
       const int k = i / BN, cidx = i % BN;
       coef[i] = cidx < prm.n ? prm.bn_save[(2 + k) * prm.n + cidx] : 0.f;
     }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -312,57 +349,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && prm.halo) {
-      // The halo tiles run ahead of the weight tiles: chunk g + (a_stages - 1) is requested while the weights
-      // of chunk g are still being issued, as soon as its ring slot is free (non-blocking test), so that the
-      // 180-row activation box is in flight for a whole chunk of MMAs before it is needed.
-      const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-      const int total_chunks = my_tiles * prm.kchunks;
-      int a_issued = 0;
-      auto issue_a = [&](bool block) -> bool {
-        if (a_issued >= total_chunks) return false;
-        const int as = a_issued % prm.a_stages;
-        const uint32_t par = ((a_issued / prm.a_stages) & 1) ^ 1;
-        if (block) mbar_wait(&a_empty[as], par);
-        else if (!mbar_test(&a_empty[as], par)) return false;
-        const int tt = blockIdx.x + (a_issued / prm.kchunks) * gridDim.x, kc = a_issued % prm.kchunks;
-        const int t = prm.rev ? num_tiles - 1 - tt : tt;
-        const int m_tile = t / prm.n_tiles;
-        const int img0 = m_tile / prm.tiles_per_img, r = m_tile % prm.tiles_per_img;
-        const int row0 = (r / prm.tiles_x) * 16, col0 = (r % prm.tiles_x) * 8;
-        mbar_expect_tx(&a_full[as], HALO_W * HALO_H * 128);
-        tma_load_4d(smem + as * HALO_TILE_BYTES, &tmA, &a_full[as], kc * 32, col0 - 1, row0 - 1, img0);
-        ++a_issued;
-        return true;
-      };
-      if (prm.halo == 2) {
-        // resident weights: the CTA keeps one n-tile for its whole life (gridDim.x is a multiple of n_tiles)
-        if (my_tiles > 0) {
-          const int t0 = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
-          const int n0 = (t0 % prm.n_tiles) * BN;
-          mbar_expect_tx(&bres_bar, 9 * prm.kchunks * B_TILE_BYTES);
-          for (int kc = 0; kc < prm.kchunks; ++kc)
-            for (int tap = 0; tap < 9; ++tap)
-              tma_load_3d(b_ring + (kc * 9 + tap) * B_TILE_BYTES, &tmB, &bres_bar, kc * 32, n0, tap);
-        }
-        while (issue_a(true)) {}
-      } else {
-        int bi = 0;
-        for (int g = 0; g < total_chunks; ++g) {
-          const int tt = blockIdx.x + (g / prm.kchunks) * gridDim.x, kc = g % prm.kchunks;
-          const int t = prm.rev ? num_tiles - 1 - tt : tt;
-          const int n0 = (t % prm.n_tiles) * BN;
-          while (a_issued <= g) issue_a(true);
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
-            if (a_issued < g + prm.a_stages) issue_a(false);
-            const int s = bi % STAGES;
-            mbar_wait(&empty_bar[s], ((bi / STAGES) & 1) ^ 1);
-            mbar_expect_tx(&full_bar[s], B_TILE_BYTES);
-            tma_load_3d(b_ring + s * B_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
-          }
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       // ring slot and barrier phase advance incrementally: no division on the issue path
       const int hw = prm.S * prm.S;
       int s = 0;
@@ -388,97 +375,90 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (prm.halo) {
-      // halo mode, same issue discipline as below: converged warp, one elected lane, incremental descriptors.
-      // With resident weights (mode 2) a chunk is ONE barrier wait followed by 36 back-to-back MMAs.
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-      const uint32_t leader = elect_one();
-      const uint64_t a_desc0 = make_desc(smem_u32(smem), 16, HALO_W * 128);
-      const uint64_t b_desc0 = make_desc(smem_u32(b_ring), 16, 1024);
-      if (prm.halo == 2 && (int)blockIdx.x < num_tiles) {
-        mbar_wait(&bres_bar, 0);
+    // The whole warp walks the loop in lock step and one elected lane issues: descriptors and barrier
+    // addresses are then warp-uniform values (uniform registers), and the per-MMA work of the issuing
+    // thread shrinks to "descriptor + 2 -> tcgen05.mma".  Computed inside an `if (lane == 0)` region every
+    // MMA cost ~16 instructions of descriptor arithmetic and uniform-register election, ~100 cycles -- more
+    // than the tensor pipe needs for an N <= 128 tile, i.e. the issue thread was the bound.
+    constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
+    const uint32_t leader = elect_one();
+    const uint64_t a_desc0 = make_desc(smem_u32(smem), 16, 1024);
+    const uint64_t b_desc0 = make_desc(smem_u32(smem) + A_TILE_BYTES, 16, 1024);
+    int s = 0, ti = 0;
+    uint32_t phase = 0;
+    uint64_t soff = 0;                                       // (s * STAGE_BYTES) >> 4, added to the address field
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
+      const int as = ti & 1;
+      mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(XF ? &ready_bar[XF ? s : 0] : &full_bar[s], phase);   // XF: wait for the transformed tile
         tc_fence_after();
+        const uint64_t ad = a_desc0 + soff, bd = b_desc0 + soff;
+        if (leader) {
+          umma_tf32(d_tmem, ad, bd, idesc, it != 0);          // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
+          umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1);
+          umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1);
+          umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1);
+          umma_commit(&empty_bar[s]);                         // frees the smem stage when these MMAs retire
+        }
+        __syncwarp();
+        soff += STAGE_BYTES >> 4;
+        if (++s == STAGES) { s = 0; soff = 0; phase ^= 1; }
       }
-      int as = 0, bs = 0, ti = 0;
-      uint32_t aph = 0, bph = 0;
-      uint64_t aoff = 0, boff = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-        const int as_acc = ti & 1;
-        mbar_wait(&acc_empty[as_acc], ((ti >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as_acc * BN);
-        for (int kc = 0; kc < prm.kchunks; ++kc) {
-          mbar_wait(&a_full[as], aph);
-          tc_fence_after();
-          const uint64_t ad = a_desc0 + aoff;
+      if (leader) umma_commit(&acc_full[as]);                // accumulator of this tile complete
+      __syncwarp();
+    }
+  } else if (XF && warp >= 2 + EW) {
+    // ===================== BN + ReLU transform of the landed A tiles =====================
+    // thread t owns logical 16-byte chunk j = t & 7 (channels kc*32 + 4j .. 4j+3) of rows (t >> 3) + 16 i:
+    // a warp covers four full 128-byte rows per step (conflict free), and the four coefficients of a thread
+    // change only with kc.
+    const int t = threadIdx.x - 32 * (2 + EW);
+    const int j = t & 7, r0 = t >> 3;
+    const int Smask = prm.S - 1;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x) {
+      const int tl = prm.rev ? num_tiles - 1 - tt : tt;
+      const int p0 = (tl / prm.n_tiles) * 128;
+      for (int tap = 0; tap < prm.taps; ++tap) {
+        int dy = 0, dx = 0;
+        if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+        // rows of this thread whose (shifted) pixel lies inside the image and the batch
+        uint32_t valid = 0;
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            // window of tap (dy,dx) = (tap/3-1, tap%3-1): shifted by (dy+1) halo rows and (dx+1) pixels of 128 bytes
-            const uint64_t at = ad + (uint64_t)(((tap / 3) * HALO_W + tap % 3) * 8);
-            uint64_t bd;
-            if (prm.halo == 2) {
-              bd = b_desc0 + (uint64_t)((kc * 9 + tap) * (B_TILE_BYTES >> 4));
-            } else {
-              mbar_wait(&full_bar[bs], bph);
-              tc_fence_after();
-              bd = b_desc0 + boff;
-            }
-            if (leader) {
-              umma_tf32(d_tmem, at, bd, idesc, (kc | tap) != 0);
-              umma_tf32(d_tmem, at + 2, bd + 2, idesc, 1);
-              umma_tf32(d_tmem, at + 4, bd + 4, idesc, 1);
-              umma_tf32(d_tmem, at + 6, bd + 6, idesc, 1);
-              if (prm.halo != 2) umma_commit(&empty_bar[bs]);   // weight tile free once these MMAs retire
-            }
-            if (prm.halo != 2) {
-              __syncwarp();
-              boff += B_TILE_BYTES >> 4;
-              if (++bs == STAGES) { bs = 0; boff = 0; bph ^= 1; }
+        for (int i = 0; i < 8; ++i) {
+          const int p = p0 + r0 + 16 * i;
+          const int x = (p & Smask) + dx, y = ((p >> prm.log2S) & Smask) + dy;
+          if (p < prm.P && (unsigned)x < (unsigned)prm.S && (unsigned)y < (unsigned)prm.S) valid |= 1u << i;
+        }
+        for (int kc = 0; kc < prm.kchunks; ++kc) {
+          const float4 sc = *reinterpret_cast<const float4*>(&coef[kc * 32 + 4 * j]);
+          const float4 sh = *reinterpret_cast<const float4*>(&coef[XF_MAX_K + kc * 32 + 4 * j]);
+          mbar_wait(&full_bar[s], ph);
+          uint8_t* a_tile = smem + s * STAGE_BYTES;
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (valid & (1u << i)) v[i] = *reinterpret_cast<const float4*>(a_tile + swz_off(r0 + 16 * i, j));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (valid & (1u << i)) {
+              float4 w = v[i];
+              w.x = round_tf32(fmaxf(fmaf(w.x, sc.x, sh.x), 0.f));
+              w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
+              w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
+              w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
+              *reinterpret_cast<float4*>(a_tile + swz_off(r0 + 16 * i, j)) = w;
             }
           }
-          if (leader) umma_commit(&a_empty[as]);               // halo tile free once all nine taps have read it
+          fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's reads
           __syncwarp();
-          aoff += HALO_TILE_BYTES >> 4;
-          if (++as == prm.a_stages) { as = 0; aoff = 0; aph ^= 1; }
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (leader) umma_commit(&acc_full[as_acc]);
-        __syncwarp();
-      }
-    } else {
-      // The whole warp walks the loop in lock step and one elected lane issues: descriptors and barrier
-      // addresses are then warp-uniform values (uniform registers), and the per-MMA work of the issuing
-      // thread shrinks to "descriptor + 2 -> tcgen05.mma".  Computed inside an `if (lane == 0)` region every
-      // MMA cost ~16 instructions of descriptor arithmetic and uniform-register election, ~100 cycles -- more
-      // than the tensor pipe needs for an N <= 128 tile, i.e. the issue thread was the bound.
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, 0, 0);
-      const uint32_t leader = elect_one();
-      const uint64_t a_desc0 = make_desc(smem_u32(smem), 16, 1024);
-      const uint64_t b_desc0 = make_desc(smem_u32(smem) + A_TILE_BYTES, 16, 1024);
-      int s = 0, ti = 0;
-      uint32_t phase = 0;
-      uint64_t soff = 0;                                       // (s * STAGE_BYTES) >> 4, added to the address field
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-        const int as = ti & 1;
-        mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
-        for (int it = 0; it < iters; ++it) {
-          mbar_wait(&full_bar[s], phase);
-          tc_fence_after();
-          const uint64_t ad = a_desc0 + soff, bd = b_desc0 + soff;
-          if (leader) {
-            umma_tf32(d_tmem, ad, bd, idesc, it != 0);          // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
-            umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1);
-            umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1);
-            umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1);
-            umma_commit(&empty_bar[s]);                         // frees the smem stage when these MMAs retire
-          }
-          __syncwarp();
-          soff += STAGE_BYTES >> 4;
-          if (++s == STAGES) { s = 0; soff = 0; phase ^= 1; }
-        }
-        if (leader) umma_commit(&acc_full[as]);                // accumulator of this tile complete
-        __syncwarp();
       }
     }
   } else {
@@ -486,14 +466,15 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
     const int ew = warp - 2;                      // epilogue warp index
     const int ci_lo = (ew >> 2) * CH_PER_WARP;    // first column chunk of this warp (two warps share a quarter)
-    uint8_t* res_buf = epi_smem + ew * EPI_BYTES_PER_WARP;
-    uint8_t* out_buf = res_buf + EPI_BOX_BYTES;   // two boxes
+    const int boxes = prm.out_bufs + (prm.has_res ? 1 : 0);
+    uint8_t* res_buf = epi_smem + ew * boxes * EPI_BOX_BYTES;
+    uint8_t* out_buf = res_buf + (prm.has_res ? EPI_BOX_BYTES : 0);   // one or two staging boxes
     float acc_s[CH_PER_WARP], acc_q[CH_PER_WARP]; // per-lane column sums (column c0 + lane), n_tiles == 1
 #pragma unroll
     for (int i = 0; i < CH_PER_WARP; ++i) acc_s[i] = acc_q[i] = 0.f;
     const bool keep_stats = prm.stats != nullptr;
     // per-channel sums can stay in registers across tiles when the CTA never changes its n-tile
-    const bool own_ntile = prm.n_tiles == 1 || prm.halo == 2;
+    const bool own_ntile = prm.n_tiles == 1;
     const int chunks_per_tile = min(BN / 32, ceil_div(prm.n, 32));   // column chunks that hold real channels
     // first tile index >= tt0 (stride gridDim.x) of this CTA in which this warp owns a real column chunk
     auto next_tile_with_work = [&](int tt0) {
@@ -506,13 +487,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
     auto prefetch_res = [&](int tt_n, int chunk) {
       const int tl = prm.rev ? num_tiles - 1 - tt_n : tt_n;
       mbar_expect_tx(&res_bar[ew], EPI_BOX_BYTES);
-      if (prm.halo) {                     // 32 TMEM lanes of this warp = 4 patch rows x 8 pixels
-        const int mt = tl / prm.n_tiles, r = mt % prm.tiles_per_img;
-        tma_load_4d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (r % prm.tiles_x) * 8,
-                    (r / prm.tiles_x) * 16 + q * 4, mt / prm.tiles_per_img);
-      } else {
-        tma_load_2d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (tl / prm.n_tiles) * 128 + q * 32);
-      }
+      tma_load_2d(res_buf, &tmR, &res_bar[ew], (tl % prm.n_tiles) * BN + chunk * 32, (tl / prm.n_tiles) * 128 + q * 32);
     };
     // residual prefetch of the first (tile, chunk) step of this warp
     int step = 0;
@@ -549,16 +524,17 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
             for (int j = 0; j < 32; ++j) v[j] += (nb + j < prm.n) ? prm.bias[nb + j] : 0.f;
           }
         }
-        float w2[32];                              // second statistic of the fused BN backward
+        float w2[XF ? 1 : 32];                     // second statistic of the fused BN backward
+        (void)w2;
         if (prm.has_res) {
           mbar_wait(&res_bar[ew], step & 1);
-          if (!bnbwd) {
+          if (XF || !bnbwd) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
               v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             }
-          } else {
+          } else if constexpr (!XF) {
             // v = dL/dh (dgrad result); the box holds the raw pre-BN activations x of this layer:
             // gm = v * 1[x*scale+shift > 0]; second statistic sum gm*x (the consumer turns the pair
             // (sum gm, sum gm*x) into sum gm*xhat = rstd*(sum gm*x - mean*sum gm) in double)
@@ -599,9 +575,16 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
             }
           }
         }
+        if (prm.round_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
+        }
         // stage the 32x32 result box (swizzled) and hand it to TMA
-        uint8_t* ob = out_buf + (step & 1) * EPI_BOX_BYTES;
-        if (lane == 0) tma_store_wait_read<1>();          // the store that used this buffer two steps ago
+        uint8_t* ob = out_buf + (prm.out_bufs == 2 ? (step & 1) * EPI_BOX_BYTES : 0);
+        if (lane == 0) {                                  // the store that last used this buffer has read it
+          if (prm.out_bufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -609,12 +592,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (prm.halo) {
-            const int r = m_tile % prm.tiles_per_img;
-            tma_store_4d(ob, &tmY, nb, (r % prm.tiles_x) * 8, (r / prm.tiles_x) * 16 + q * 4, m_tile / prm.tiles_per_img);
-          } else {
-            tma_store_2d(ob, &tmY, nb, prow0);            // rows >= P and columns >= n are clipped by the map
-          }
+          tma_store_2d(ob, &tmY, nb, prow0);              // rows >= P and columns >= n are clipped by the map
           tma_store_commit();
         }
         ++step;
@@ -625,7 +603,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
           const int rows_valid = min(32, prm.P - prow0);
           const int jc = lane >> 2, wc = (lane & 3) * 4;
           float s1 = 0.f, s2 = 0.f;
-          if (!bnbwd) {
+          if (XF || !bnbwd) {
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
               float val = *reinterpret_cast<const float*>(ob + swz_off(r, jc) + wc);
@@ -633,7 +611,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
               s1 += val;
               s2 = fmaf(val, val, s2);
             }
-          } else {
+          } else if constexpr (!XF) {
             // second statistic of the fused BN backward: sum gm * x, x = raw activations still in res_buf
             // (the next residual prefetch targets the same buffer: it was issued after all lanes had
             // read x into registers, so re-reading here would race -- use the register copy instead)
@@ -675,15 +653,13 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, TcCfg<BN>::MIN_CTAS) conv_
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
       const int tt = threadIdx.x - 64;
-      const int t_first = prm.rev ? num_tiles - 1 - (int)blockIdx.x : (int)blockIdx.x;
-      const int n0_cta = (t_first % prm.n_tiles) * BN;       // the n-tile this CTA kept for all its tiles
       for (int c = tt; c < BN; c += 32 * EW) {
-        if (n0_cta + c < prm.n) {
+        if (c < prm.n) {                                     // n_tiles == 1: column index == channel index
           float s1 = 0.f, s2 = 0.f;
 #pragma unroll
           for (int w = 0; w < EW; ++w) { s1 += red_sum[w][c]; s2 += red_sq[w][c]; }
-          atomicAdd(&prm.stats[n0_cta + c], (double)s1);
-          atomicAdd(&prm.stats[prm.n + n0_cta + c], (double)s2);
+          atomicAdd(&prm.stats[c], (double)s1);
+          atomicAdd(&prm.stats[prm.n + c], (double)s2);
         }
       }
     }
@@ -701,14 +677,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+  static EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return (EncodeTiledFn) nullptr;
+  }();                                            // thread-safe (magic static): autograd's thread may be first
   return fn;
 }
 
@@ -762,118 +738,91 @@ static int make_row_map(CUtensorMap* m, const float* base, int P, int n, int ld)
   return encode_map(m, base, 2, dims, strides, box);
 }
 
-// 4-D map over a [B][S][S][ld] fp32 tensor exposing `n` real channels, (32 ch, 8, 4, 1) boxes: the 32 TMEM
-// lanes one epilogue warp owns in halo mode (4 patch rows x 8 pixels)
-static int make_patch_map(CUtensorMap* m, const float* base, int B, int S, int n, int ld) {
-  cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4};
-  cuuint32_t box[4] = {32, 8, 4, 1};
-  return encode_map(m, base, 4, dims, strides, box);
+static int env_int(const char* name, int lo, int hi, int dflt) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int v = atoi(e);
+  return v >= lo && v <= hi ? v : dflt;
 }
 
-// Opt-in (RNVP_HALO=1).  The path is correct (tests/test_gpu_ops.py::test_conv_tf32_halo) and cuts the
-// shared-memory feed of a 3x3 conv by 2-3x.  Measured on B200 (batch 256, forward): S = 64, 32 channels
-// (resident weights, one barrier wait + 36 back-to-back MMAs per tile) 83 us against 97 us for nine
-// tap-shifted loads; S = 32, 64 channels 79 us against 64 us (two 32-wide n-tiles double the MMA count);
-// S = 16, 128 channels 50 against 52 us.  83 us is the tensor-pipe floor of that layer: an M = 128, K = 8
-// kind::tf32 MMA occupies the pipe for ~65 + 0.5 N cycles (82 at N = 32), so 36 of them per 128-pixel tile
-// take 1.5 us x 55 tiles per SM.  It stays off by default: the gain is 0.4 ms per training step and the
-// resident-weight variant runs one CTA per SM.
-static bool halo_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("RNVP_HALO");
-    on = (e && e[0] == '1') ? 1 : 0;
-  }
-  return on != 0;
+// per-instantiation launch facts, computed once (thread-safe: C++11 magic static)
+struct FwdKernelInfo {
+  int max_stages = 0, by_regs = 0, static_smem = 0;
+  int status = RNVP_OK;
+};
+template <int BN, int XF>
+static const FwdKernelInfo& fwd_kernel_info() {
+  static const FwdKernelInfo info = [] {
+    FwdKernelInfo k;
+    constexpr int THREADS = TcCfg<BN, XF>::THREADS;
+    const char* name = XF ? (BN == 128 ? "RNVP_TC_XSTAGES_128" : (BN == 64 ? "RNVP_TC_XSTAGES_64" : "RNVP_TC_XSTAGES_32"))
+                          : (BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
+    k.max_stages = env_int(name, 1, TC_MAX_STAGES, TcCfg<BN, XF>::STAGES);
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN, XF>) != cudaSuccess) { k.status = RNVP_ERR_CUDA; return k; }
+    k.by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
+    k.static_smem = (int)fa.sharedSizeBytes;
+    if (cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             227 * 1024 - k.static_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+      k.status = RNVP_ERR_CUDA;
+    return k;
+  }();
+  return info;
 }
-// 3x3 convs on feature maps of at least 16 x 16 (sides a multiple of 16) take the halo path
-static bool use_halo(const ConvArgs& a) { return halo_enabled() && a.taps == 9 && a.S >= 16 && a.S % 16 == 0; }
 
-template <int BN>
+template <int BN, int XF>
 static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmY, tmR;
-  const bool halo = use_halo(a);
   int bw = 0, bh = 0, bn = 0;
   pixel_box(a.S, 128, &bw, &bh, &bn);
-  if (halo) RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, HALO_W, HALO_H, 1));
-  else RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
+  RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
   cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
   cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
   const float* rsrc = a.bn_x ? a.bn_x : a.res;
-  if (halo) {
-    RNVP_TRY(make_patch_map(&tmY, a.y, a.B, a.S, a.n, a.ldy));
-    if (rsrc) RNVP_TRY(make_patch_map(&tmR, rsrc, a.B, a.S, a.n, a.ldy));
-  } else {
-    RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
-    if (rsrc) RNVP_TRY(make_row_map(&tmR, rsrc, prm.P, a.n, a.ldy));
-  }
-  if (!rsrc) tmR = tmY;
-  constexpr int THREADS = TcCfg<BN>::THREADS;
-  constexpr int EPI = TcCfg<BN>::EPI_WARPS * EPI_BYTES_PER_WARP;
-  // shared-memory plan of this launch.  mode 0 flat: ring of (A + B) stages.  mode 1 halo, streamed weights:
-  // A ring of halo tiles + B ring (BN = 32 keeps two CTAs per SM, the wider tiles run one).  mode 2 halo,
-  // resident weights (BN = 32, <= 64 input channels): all 9 * kchunks weight tiles of the CTA's n-tile stay in
-  // shared memory, one CTA per SM, a deeper A ring.
-  const int kchunks = a.kpad / 32;
-  const int mode = !halo ? 0 : (BN == 32 && kchunks <= 2 ? 2 : 1);
-  static int flat_stages = 0;
-  static int by_regs = 0, static_smem = 0;
-  if (!flat_stages) {
-    flat_stages = TcCfg<BN>::STAGES;
-    const char* e = getenv(BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
-    if (e && atoi(e) >= 1 && atoi(e) <= TC_MAX_STAGES) flat_stages = atoi(e);
-    cudaFuncAttributes fa;
-    RNVP_CUDA(cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN>));
-    by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
-    static_smem = (int)fa.sharedSizeBytes;
-    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   227 * 1024 - static_smem));
-    RNVP_CUDA(cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   cudaSharedmemCarveoutMaxShared));
-  }
-  int smem;
-  if (mode == 0) {
-    prm.stages = flat_stages; prm.a_stages = 0; prm.b_tiles = 0;
-    smem = flat_stages * (A_TILE_BYTES + BN * 128) + EPI + 1024;
-  } else if (mode == 1) {
-    prm.a_stages = BN == 64 ? 3 : 2;
-    prm.stages = BN == 32 ? 3 : (BN == 64 ? 8 : 4);
-    prm.b_tiles = prm.stages;
-    smem = prm.a_stages * HALO_TILE_BYTES + prm.b_tiles * BN * 128 + EPI + 1024;
-  } else {
-    prm.a_stages = kchunks == 1 ? 4 : 3;
-    prm.stages = 1;
-    prm.b_tiles = 9 * kchunks;
-    smem = prm.a_stages * HALO_TILE_BYTES + prm.b_tiles * BN * 128 + EPI + 1024;
-  }
-  RNVP_REQUIRE(smem + static_smem <= 227 * 1024, "conv: shared-memory plan of %d bytes does not fit", smem);
+  RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
+  if (rsrc) RNVP_TRY(make_row_map(&tmR, rsrc, prm.P, a.n, a.ldy));
+  else tmR = tmY;
+  constexpr int THREADS = TcCfg<BN, XF>::THREADS;
+  const FwdKernelInfo& ki = fwd_kernel_info<BN, XF>();
+  RNVP_REQUIRE(ki.status == RNVP_OK, "conv: cudaFuncGetAttributes / cudaFuncSetAttribute failed");
+  // shared-memory plan: epilogue staging (a residual box only when the layer has one; one output box per warp
+  // for the 32-wide tile, whose warps stage one box per tile) + as many ring stages as keep MIN_CTAS resident
+  prm.out_bufs = env_int("RNVP_TC_OUTBUFS", 1, 2, BN == 32 ? 1 : 2);
+  const int EPI = TcCfg<BN, XF>::EPI_WARPS * (prm.out_bufs + (prm.has_res ? 1 : 0)) * EPI_BOX_BYTES;
+  const int budget = (228 * 1024) / TcCfg<BN, XF>::MIN_CTAS - 1024 /* driver */ - ki.static_smem - 1024 /* alignment */;
+  int stages = (budget - EPI) / (A_TILE_BYTES + BN * 128);
+  if (stages > ki.max_stages) stages = ki.max_stages;
+  if (stages < 2) stages = 2;
+  prm.stages = stages;
+  const int smem = stages * (A_TILE_BYTES + BN * 128) + EPI + 1024;
+  RNVP_REQUIRE(smem + ki.static_smem <= 227 * 1024, "conv: shared-memory plan of %d bytes does not fit", smem);
   // resident CTAs per SM from the kernel's own footprint: shared memory (dynamic + static + 1 KB the driver
   // reserves per CTA) against the 228 KB of an SM, registers against the 64 K file, TMEM columns
   // (cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports this kernel: it answered 1 where 2 fit)
-  int ctas = (228 * 1024) / (smem + static_smem + 1024);
-  if (ctas > by_regs) ctas = by_regs;
+  int ctas = (228 * 1024) / (smem + ki.static_smem + 1024);
+  if (ctas > ki.by_regs) ctas = ki.by_regs;
   if (ctas > 512 / (2 * BN < 32 ? 32 : 2 * BN)) ctas = 512 / (2 * BN < 32 ? 32 : 2 * BN);
   if (ctas < 1) ctas = 1;
-  if (const char* e2 = getenv("RNVP_TC_CTAS")) { if (atoi(e2) >= 1) ctas = atoi(e2); }
-  static bool said[3] = {false, false, false};
-  if (!said[mode] && getenv("RNVP_DEBUG")) {
-    said[mode] = true;
-    fprintf(stderr, "[rnvp] conv_fwd_tf32<%d> mode %d: A stages %d, B tiles %d, smem %d+%d, regs -> %d, => %d CTAs/SM\n", BN,
-            mode, prm.a_stages, mode ? prm.b_tiles : prm.stages, smem, static_smem, by_regs, ctas);
+  ctas = env_int("RNVP_TC_CTAS", 1, 8, ctas);
+  if (getenv("RNVP_DEBUG")) {
+    static bool said[2][3] = {};
+    bool& s = said[XF][BN == 32 ? 0 : (BN == 64 ? 1 : 2)];
+    if (!s) {
+      s = true;
+      fprintf(stderr, "[rnvp] conv_fwd_tf32<%d,%d>: %d stages, smem %d+%d, regs -> %d, => %d CTAs/SM\n", BN, XF, stages,
+              smem, ki.static_smem, ki.by_regs, ctas);
+    }
   }
-  prm.halo = mode;
-  prm.tiles_x = a.S / 8;
-  prm.tiles_per_img = (a.S / 8) * (a.S / 16);
   prm.m_tiles = ceil_div(prm.P, 128);
   prm.n_tiles = ceil_div(a.n, BN);
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas;
   if (grid > tiles) grid = tiles;
-  if (mode == 2) grid -= grid % prm.n_tiles;          // a CTA must keep one n-tile: its weights are resident
-  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
+  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN, XF>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -882,13 +831,15 @@ bool conv_tf32_fusable(const ConvArgs& a) {
   int bw, bh, bn;
   return pixel_box(a.S, 128, &bw, &bh, &bn) && a.kpad % 32 == 0 && a.ldy % 4 == 0 && a.n <= 512;
 }
+// the BN prologue additionally keeps 2 * kpad coefficients in shared memory
+bool conv_tf32_prologue_ok(const ConvArgs& a) { return conv_tf32_fusable(a) && a.kpad <= XF_MAX_K; }
 
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   const int P = a.B * a.S * a.S;
   if (P == 0) return RNVP_OK;
   int bw, bh, bn;
   if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0) {
-    RNVP_REQUIRE(a.bn_x == nullptr, "fused BN-backward epilogue needs the tensor-core kernel");
+    RNVP_REQUIRE(a.bn_x == nullptr && a.xf == nullptr, "fused BN prologue / backward epilogue need the tensor-core kernel");
     return k_conv_fwd_fp32(a, st);          // shapes the TMA box cannot express: CUDA-core kernel
   }
   RNVP_REQUIRE(a.bn_x == nullptr || (a.res == nullptr && a.bias == nullptr && a.n % 4 == 0 && a.bn_save && a.stats),
@@ -899,15 +850,28 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   ConvTcParams prm{};
   prm.bias = a.bias; prm.has_res = a.res != nullptr || a.bn_x != nullptr; prm.stats = a.stats;
   prm.bn_save = a.bn_x ? a.bn_save : nullptr;
+  prm.round_out = a.round_out;
   prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
+  prm.log2S = 0;
+  while ((1 << prm.log2S) < a.S) ++prm.log2S;
   prm.rev = next_sweep_dir();
-  if (a.n <= 32) return launch_fwd<32>(a, prm, st);
-  // 3x3 halo convs with <= 64 input and output channels: two 32-wide n-tiles with resident weights beat one
-  // 64-wide tile with streamed weights (the weight tiles, not the activations, dominate the smem feed)
-  if (a.n <= 64 && use_halo(a) && a.kpad <= 64) return launch_fwd<32>(a, prm, st);
-  if (a.n <= 64) return launch_fwd<64>(a, prm, st);
-  return launch_fwd<128>(a, prm, st);
+  if (a.xf) {
+    const BnPrologue& x = *a.xf;
+    RNVP_REQUIRE(a.bn_x == nullptr, "BN prologue and BN-backward epilogue are separate kernels");
+    RNVP_REQUIRE(a.kpad <= XF_MAX_K && x.C <= a.kpad, "BN prologue: %d input channels unsupported (max %d)", x.C, XF_MAX_K);
+    RNVP_REQUIRE(x.mode == 2 ? x.save != nullptr : (x.gamma && x.beta && x.run_mean && x.run_var),
+                 "BN prologue: missing coefficient source");
+    RNVP_REQUIRE(x.mode != 1 || (x.sums && x.save), "BN prologue: training mode needs sums and save");
+    prm.xf_mode = x.mode; prm.xf_C = x.C; prm.xf_sums = x.sums; prm.xf_count = x.count;
+    prm.xf_gamma = x.gamma; prm.xf_beta = x.beta; prm.xf_rm = x.run_mean; prm.xf_rv = x.run_var; prm.xf_save = x.save;
+    if (a.n <= 32) return launch_fwd<32, 1>(a, prm, st);
+    if (a.n <= 64) return launch_fwd<64, 1>(a, prm, st);
+    return launch_fwd<128, 1>(a, prm, st);
+  }
+  if (a.n <= 32) return launch_fwd<32, 0>(a, prm, st);
+  if (a.n <= 64) return launch_fwd<64, 0>(a, prm, st);
+  return launch_fwd<128, 0>(a, prm, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -924,6 +888,7 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
 // (column sums of dy) is taken from the staged dy boxes in shared memory by the epilogue warps, which
 // are otherwise idle during the main loop -- it costs no tensor-core work and no extra traffic.
 // ---------------------------------------------------------------------------------------------
+constexpr int TC_THREADS = 192;               // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue (+ BN transform of the x boxes)
 constexpr int WG_BOX_BYTES = 64 * 128;        // 64 pixels x 32 fp32
 constexpr int WG_MAX_STAGES = 16;              // ring depths are chosen per launch from the actual stage sizes
 constexpr int WG_RING_BYTES = 192 * 1024;     // A ring + B ring
@@ -942,6 +907,10 @@ struct WgradTcParams {
   int a_stages, b_stages, a_stage_bytes, b_stage_bytes;
   int ring_bytes;                           // A ring + MMA slack + B ring
   int a_lbo;                                // byte stride between the 32-row groups of the A operand
+  // BN prologue: x in HBM is the raw pre-BN activation of the forward conv; the epilogue warps (idle during the
+  // main loop) rewrite every landed x box to tf32(relu(x * scale + shift)) with the coefficients the forward saved
+  const float* xf_save;                     // [4C] mean, rstd, scale, shift, or null
+  int xf_C, log2S;
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
@@ -963,10 +932,13 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   uint8_t* b_ring = smem + prm.ring_bytes - WG_B_STAGES * WG_B_STAGE_BYTES;
   __shared__ __align__(8) uint64_t a_full[WG_MAX_STAGES], a_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t b_full[WG_MAX_STAGES], b_empty[WG_MAX_STAGES];
+  __shared__ __align__(8) uint64_t a_ready[WG_MAX_STAGES];            // BN prologue: x boxes of the stage transformed
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float wcoef[2][128];                       // (scale | shift) of this CTA's k-tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool xf = prm.xf_save != nullptr;
   int bx = blockIdx.x;
   const int kt = bx % prm.k_tiles; bx /= prm.k_tiles;
   const int nt = bx % prm.n_tiles; bx /= prm.n_tiles;
@@ -985,7 +957,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmDy);
     prefetch_tmap(&tmX);
-    for (int s = 0; s < WG_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < WG_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], 4); }
     // a dy stage is released by the MMA commit and, when this CTA owns the bias gradient, by the four
     // epilogue warps that read the boxes for the column sums
     for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], do_bias ? 5 : 1); }
@@ -995,6 +967,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   if (warp == 1) tmem_alloc_dyn(&tmem_base_slot, (uint32_t)prm.tmem_cols);
   pdl_wait();                                // the prologue above overlaps the previous kernel's tail
   pdl_trigger();                             // after the wait: at most one successor in flight (see conv kernel)
+  if (xf)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      const int c = k0 + (i & 127);
+      wcoef[i >> 7][i & 127] = c < prm.xf_C ? prm.xf_save[(2 + (i >> 7)) * prm.xf_C + c] : 0.f;
+    }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1054,7 +1031,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
           const uint64_t bd = b_desc0 + boff;
           const uint32_t acc = (t != t_begin);
           for (int mg = 0; mg < groups; ++mg) {
-            mbar_wait(&a_full[as], aph);
+            mbar_wait(xf ? &a_ready[as] : &a_full[as], aph);
             tc_fence_after();
             const uint64_t ad = a_desc0 + aoff;
             const uint32_t d = tmem_base + (uint32_t)(mg * N);
@@ -1083,23 +1060,75 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       const int m = q * 32 + lane;               // accumulator row = (tap_local, k)
       const int kc = kb * 32;
       const int tl = m / kc, k = m % kc;
-      if (do_bias) {
-        // dbias[n] = sum_p dy[p,n]: warp q owns dy box q (32 channels x 64 pixel rows of 128 bytes).  Within a
-        // row the four 32-byte chunks are XOR-permuted by (row & 3) ("128B swizzle, 32B atom" = Swizzle<2,5,2>),
-        // so lane w accumulates word w separately per row phase and un-permutes at the end.
+      if (do_bias || xf) {
+        // Main-loop duties of the otherwise idle epilogue warps, tile by tile in the producer's order:
+        //  (a) dbias[n] = sum_p dy[p,n]: warp q owns dy box q (32 channels x 64 pixel rows of 128 bytes).  Within a
+        //      row the four 32-byte chunks are XOR-permuted by (row & 3) ("128B swizzle, 32B atom" = Swizzle<2,5,2>),
+        //      so lane w accumulates word w separately per row phase and un-permutes at the end.
+        //  (b) BN prologue: every landed x box -> tf32(relu(x * scale + shift)) in place.  Thread e owns physical
+        //      16-byte chunk e & 7 of rows (e >> 3) + 16 i: the row phase (row & 3) is fixed per thread, hence so are
+        //      its four logical channels within a box.  Rows whose tap-shifted pixel lies outside the image were
+        //      zero-filled by TMA and stay zero (the forward conv pads the ACTIVATED tensor).
         float part[4] = {0.f, 0.f, 0.f, 0.f};
+        const int e = threadIdx.x - 64;
+        const int c16 = e & 7, er0 = e >> 3;
+        const int lch = 8 * ((c16 >> 1) ^ (er0 & 3)) + 4 * (c16 & 1);     // logical channel (within a box) of this chunk
+        const int Smask = prm.S - 1;
+        int as = 0;
+        uint32_t aph = 0;
         for (int t = t_begin; t < t_end; ++t) {
-          const int bi = t - t_begin, bs = bi % WG_B_STAGES;
-          mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
-          if (q < nbx) {
-            const float* box = reinterpret_cast<const float*>(b_ring + bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES);
+          if (do_bias) {
+            const int bi = t - t_begin, bs = bi % WG_B_STAGES;
+            mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+            if (q < nbx) {
+              const float* box = reinterpret_cast<const float*>(b_ring + bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES);
 #pragma unroll 16
-            for (int r = 0; r < 64; ++r) part[r & 3] += box[r * 32 + lane];
+              for (int r = 0; r < 64; ++r) part[r & 3] += box[r * 32 + lane];
+            }
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_empty[bs])) : "memory");
           }
-          __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_empty[bs])) : "memory");
+          if (xf) {
+            for (int mg = 0; mg < groups; ++mg) {
+              const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);
+              mbar_wait(&a_full[as], aph);
+              for (int tli = 0; tli < tl_n; ++tli) {
+                const int tap = tap0 + mg * prm.tpm + tli;
+                int dy = 0, dx = 0;
+                if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+                uint32_t valid = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int p = t * 64 + er0 + 16 * i;
+                  const int x = (p & Smask) + dx, y = ((p >> prm.log2S) & Smask) + dy;
+                  if (p < prm.P && (unsigned)x < (unsigned)prm.S && (unsigned)y < (unsigned)prm.S) valid |= 1u << i;
+                }
+                for (int j = 0; j < kb; ++j) {
+                  uint8_t* box = a_ring + as * WG_A_STAGE_BYTES + (tli * kb + j) * WG_BOX_BYTES;
+                  const float4 sc = *reinterpret_cast<const float4*>(&wcoef[0][32 * j + lch]);
+                  const float4 sh = *reinterpret_cast<const float4*>(&wcoef[1][32 * j + lch]);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (valid & (1u << i)) {
+                      float4* ptr = reinterpret_cast<float4*>(box + (er0 + 16 * i) * 128 + c16 * 16);
+                      float4 w = *ptr;
+                      w.x = round_tf32(fmaxf(fmaf(w.x, sc.x, sh.x), 0.f));
+                      w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
+                      w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
+                      w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
+                      *ptr = w;
+                    }
+                  }
+                }
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_ready[as])) : "memory");
+              if (++as == WG_A_STAGES) { as = 0; aph ^= 1; }
+            }
+          }
         }
-        if (q < nbx) {
+        if (do_bias && q < nbx) {
 #pragma unroll
           for (int ph = 0; ph < 4; ++ph) {
             const int ch = n0 + q * 32 + ((((lane >> 3) ^ ph) << 3) | (lane & 7));
@@ -1130,12 +1159,19 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   if (warp == 1) tmem_dealloc_dyn(tmem_base, (uint32_t)prm.tmem_cols);
 }
 
+bool wgrad_tf32_prologue_ok(const WgradArgs& a) {
+  int bw, bh, bn;
+  return pixel_box(a.S, 64, &bw, &bh, &bn) && a.kpad % 32 == 0 && a.lddy % 32 == 0;
+}
+
 int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   const int P = a.B * a.S * a.S;
   if (P == 0) return RNVP_OK;
   int bw, bh, bn;
-  if (!pixel_box(a.S, 64, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.lddy % 32 != 0)
+  if (!pixel_box(a.S, 64, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.lddy % 32 != 0) {
+    RNVP_REQUIRE(a.xf_save == nullptr, "wgrad BN prologue needs the tensor-core kernel");
     return k_conv_wgrad_fp32(a, st);
+  }
   RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "wgrad: taps=%d", a.taps);
   CUtensorMap tmDy, tmX;
   // MN-major fp32 operands: 128B swizzle with 32-byte atoms (the only layout tcgen05 accepts for them)
@@ -1144,6 +1180,9 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   WgradTcParams prm{};
   prm.dw = a.dw; prm.dbias = a.dbias;
   prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = a.kpad; prm.taps = a.taps; prm.S = a.S;
+  prm.xf_save = a.xf_save; prm.xf_C = a.xf_C;
+  prm.log2S = 0;
+  while ((1 << prm.log2S) < a.S) ++prm.log2S;
   prm.n_tiles = ceil_div(a.n, 128);
   prm.k_tiles = ceil_div(a.kpad, 128);
   prm.kb = (a.kpad < 128 ? a.kpad : 128) / 32;

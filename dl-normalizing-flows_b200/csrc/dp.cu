@@ -84,7 +84,11 @@ int plan_num_couplings(const rnvp_plan* p);
 // in rank order (so all ranks obtain bit-identical sums).  Inbox slots alternate with the parity of the
 // sequence number: a rank can only be one exchange ahead of the slowest one, because finishing exchange k+1
 // needs every peer's flag k+1, which a peer publishes only after it has finished reading exchange k.
-// A peer that never arrives trips a ~2 s timeout and is counted in `err` instead of hanging the GPU.
+// A rank may legitimately lag by seconds (checkpoint save, logging, a dataloader stall, first-call module load),
+// so the wait is LONG (~2 minutes of spinning); if it still expires, or a peer's sequence number is more than
+// one ahead (the ranks issued different numbers of exchanges), the kernel poisons its result with NaN and sets a
+// STICKY error word in mapped host memory: every later rnvp_flow_* / rnvp_coupling_* call of the plan fails with
+// RNVP_ERR_STATE (make_ctx checks the word), instead of silently training on wrong statistics.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kXchgThreads = 256;
 __device__ __forceinline__ size_t xchg_flag_off(int world, int cap) { return (size_t)world * 2 * cap * sizeof(double); }
@@ -92,6 +96,8 @@ __device__ __forceinline__ size_t xchg_flag_off(int world, int cap) { return (si
 __global__ void __launch_bounds__(kXchgThreads) stats_exchange_kernel(void* const* __restrict__ peers, int rank, int world,
                                                                       int cap, double* __restrict__ buf, int n,
                                                                       unsigned long long seq, int* err) {
+  __shared__ int failed;
+  if (threadIdx.x == 0) failed = 0;
   const int slot = (int)(seq & 1ull);
   // 1. push: my vector into slot [rank][slot] of every rank's inbox (my own included)
   for (int p = 0; p < world; ++p) {
@@ -112,10 +118,19 @@ __global__ void __launch_bounds__(kXchgThreads) stats_exchange_kernel(void* cons
     while (true) {
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
       if (v >= seq) break;
-      if (clock64() - t0 > 4000000000ll) { atomicAdd(err, 1); break; }      // ~2 s at 2 GHz: a peer is gone
+      if (clock64() - t0 > 240000000000ll) break;                           // ~2 min at 2 GHz: the peer is gone
     }
+    // a healthy peer is at `seq` or one exchange ahead; anything else is a timeout (1) or a desynchronised
+    // call sequence (2): e.g. one rank ran an extra train-mode forward
+    if (v < seq) { failed = 1; *reinterpret_cast<volatile int*>(err) = 1; }
+    else if (v > seq + 1) { failed = 1; *reinterpret_cast<volatile int*>(err) = 2; }
   }
   __syncthreads();
+  if (failed) {
+    __threadfence_system();
+    for (int i = threadIdx.x; i < n; i += kXchgThreads) buf[i] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
   // 4. reduce in rank order
   const double* inbox = reinterpret_cast<const double*>(peers[rank]);
   for (int i = threadIdx.x; i < n; i += kXchgThreads) {
@@ -138,6 +153,28 @@ int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st) {
   RNVP_REQUIRE(dp->comm != nullptr, "data-parallel communicator not initialised");
   RNVP_NCCL(g_nccl.AllReduce(buf, buf, n, ncclFloat64_, ncclSum_, (ncclComm_t)dp->comm, st));
   return RNVP_OK;
+}
+
+// Synchronised batch norm and the gradient average assume that every rank holds the same local batch (count =
+// local pixels * world, ncclAvg).  Each training forward therefore reduces (B, B^2) over the ranks first; equal
+// batches <=> world * sum B^2 == (sum B)^2.  A mismatch sets the sticky error word (3).
+__global__ void batch_check_kernel(const double* v, int world, int* err) {
+  const double s1 = v[0], s2 = v[1];
+  if (s1 != s1 || fabs((double)world * s2 - s1 * s1) > 0.5) *reinterpret_cast<volatile int*>(err) = (s1 != s1) ? 1 : 3;
+}
+int dp_check_equal_batches(DpState* dp, int batch, double* scratch2, cudaStream_t st) {
+  if (dp->world <= 1) return RNVP_OK;
+  const double h[2] = {(double)batch, (double)batch * (double)batch};
+  RNVP_CUDA(cudaMemcpyAsync(scratch2, h, sizeof(h), cudaMemcpyHostToDevice, st));
+  RNVP_TRY(dp_allreduce_doubles(dp, scratch2, 2, st));
+  if (dp->xchg_err) {
+    batch_check_kernel<<<1, 1, 0, st>>>(scratch2, dp->world, dp->xchg_err);
+    RNVP_LAUNCH_CHECK();
+  }
+  return RNVP_OK;
+}
+int dp_sticky_error(const DpState* dp) {
+  return dp->xchg_err_host ? *reinterpret_cast<volatile int*>(dp->xchg_err_host) : 0;
 }
 
 static int launch_bucket(DpState* dp, int64_t begin, int64_t end, cudaStream_t main) {
@@ -211,8 +248,9 @@ int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64) {
   const size_t bytes = (size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)dp->world * sizeof(unsigned long long);
   RNVP_CUDA(cudaMalloc(&dp->xchg_local, bytes));
   RNVP_CUDA(cudaMemset(dp->xchg_local, 0, bytes));
-  RNVP_CUDA(cudaMalloc(&dp->xchg_err, sizeof(int)));
-  RNVP_CUDA(cudaMemset(dp->xchg_err, 0, sizeof(int)));
+  RNVP_CUDA(cudaHostAlloc(&dp->xchg_err_host, sizeof(int), cudaHostAllocMapped));
+  *dp->xchg_err_host = 0;
+  RNVP_CUDA(cudaHostGetDevicePointer(&dp->xchg_err, dp->xchg_err_host, 0));
   RNVP_CUDA(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   RNVP_CUDA(cudaIpcGetMemHandle(&h, dp->xchg_local));
@@ -242,15 +280,14 @@ int rnvp_dp_xchg_open(rnvp_plan* plan, const void* all_handles) {
   return RNVP_OK;
 }
 
-// exchanges that gave up waiting for a peer since the last call (0 in a healthy run); -1 when not in use
+// sticky error word of the statistic exchange: 0 healthy, 1 a peer never arrived, 2 the ranks' call sequences
+// diverged, 3 the ranks' local batch sizes differ; -1 when the exchange is not in use.  Reading costs nothing (the
+// word lives in mapped host memory); it is never cleared: the communicator must be rebuilt.
 int rnvp_dp_xchg_errors(rnvp_plan* plan) {
   if (!plan) return -1;
   rnvp::DpState* dp = rnvp::plan_dp(plan);
-  if (!dp->xchg_ready) return -1;
-  int e = 0;
-  if (cudaMemcpy(&e, dp->xchg_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  cudaMemset(dp->xchg_err, 0, sizeof(int));
-  return e;
+  if (!dp->xchg_err_host) return -1;
+  return *reinterpret_cast<volatile int*>(dp->xchg_err_host);
 }
 
 int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets_host, int64_t bucket_elems) {
@@ -286,8 +323,8 @@ int rnvp_dp_finalize(rnvp_plan* plan) {
       if (dp->xchg_peer_host[r]) { cudaIpcCloseMemHandle(dp->xchg_peer_host[r]); dp->xchg_peer_host[r] = nullptr; }
     if (dp->xchg_peers_dev) cudaFree(dp->xchg_peers_dev);
     cudaFree(dp->xchg_local);
-    cudaFree(dp->xchg_err);
-    dp->xchg_peers_dev = nullptr; dp->xchg_local = nullptr; dp->xchg_err = nullptr;
+    if (dp->xchg_err_host) cudaFreeHost(dp->xchg_err_host);
+    dp->xchg_peers_dev = nullptr; dp->xchg_local = nullptr; dp->xchg_err = nullptr; dp->xchg_err_host = nullptr;
   }
   delete[] dp->off;
   dp->off = nullptr;

@@ -407,7 +407,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     float4* dx, const float4* add, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
-                                    float* dbeta, float inv_world, int raw_x_sums, int rev) {
+                                    float* dbeta, float inv_world, int raw_x_sums, int rnd, int rev) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
@@ -461,18 +461,18 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
       if (add) {
         r[0] += ov[u].x; r[1] += ov[u].y; r[2] += ov[u].z; r[3] += ov[u].w;
       }
-      dx[e] = make_float4(r[0], r[1], r[2], r[3]);
+      dx[e] = make_float4(maybe_round(r[0], rnd), maybe_round(r[1], rnd), maybe_round(r[2], rnd), maybe_round(r[3], rnd));
     }
   }
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st) {
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, (const float4*)add, n4, C, ld,
-                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, next_sweep_dir()));
+                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, tf32_round, next_sweep_dir()));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

@@ -42,9 +42,10 @@ int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C,
                     const float* save, double* sums2, cudaStream_t st);
 // dx = gamma*rstd*(gm - m1 - xhat*m2) (+ add, which may alias dx); block 0 adds dgamma/dbeta.
 // raw_x_sums: sums2[C:2C] holds sum gm*x (fused dgrad epilogue) instead of sum gm*xhat
+// tf32_round: dx is the dy operand of a dgrad / wgrad MMA -> round to nearest TF32
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, cudaStream_t st);
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st);
 
 // ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
@@ -126,16 +127,32 @@ struct DpState {
   void* xchg_peer_host[16] = {};     // opened peer mappings (to close them)
   int xchg_cap = 0;                  // doubles per slot
   unsigned long long xchg_seq = 0;   // exchanges issued so far (all ranks call in the same order)
-  int* xchg_err = nullptr;           // device: number of exchanges that timed out waiting for a peer
+  int* xchg_err = nullptr;           // device alias of the sticky error word (0 healthy; see rnvp_dp_xchg_errors)
+  int* xchg_err_host = nullptr;      // the word itself, in mapped host memory
   bool xchg_ready = false;
 };
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st);
+// reduce (B, B^2) over the ranks and flag unequal local batches in the sticky error word (scratch2: 2 device doubles)
+int dp_check_equal_batches(DpState* dp, int batch, double* scratch2, cudaStream_t st);
+int dp_sticky_error(const DpState* dp);   // current value of the sticky error word (host read, no synchronisation)
 // called after the backward of coupling `ci` was enqueued on `main` (couplings finish last -> first)
 int dp_coupling_done(DpState* dp, int ci, cudaStream_t main);
 // make `main` wait for every gradient bucket launched during this backward
 int dp_join(DpState* dp, cudaStream_t main);
 
 // ---- convolutions -------------------------------------------------------------------
+// BatchNorm2d + ReLU folded into a tensor-core kernel's operand path: the operand in HBM is the raw pre-BN tensor
+struct BnPrologue {
+  int mode;            // 1 batch statistics (sums), 0 running statistics, 2 coefficients read back from `save`
+  int C;               // real channels
+  const double* sums;  // [2C] sum, sum of squares over `count` values (mode 1)
+  double count;
+  const float* gamma;
+  const float* beta;
+  float* run_mean;     // updated in mode 1
+  float* run_var;
+  float* save;         // [4C] mean, rstd, scale, shift: written in mode 1, read in mode 2
+};
 struct ConvArgs {
   const float* x;      // [B,S,S,kpad] activated input
   const float* w;      // [taps][npad][kpad]
@@ -148,17 +165,28 @@ struct ConvArgs {
   // stats = (sum y, sum y * xhat) with the coefficients of bn_save = (mean, rstd, scale, shift)[n]
   const float* bn_x = nullptr;     // [P,ldy] raw pre-BN activations
   const float* bn_save = nullptr;  // [4n]
+  // TF32 tier: y is read raw by another conv MMA (trunk a_i -> skip convs / wgrads, d a_i -> dgrads / wgrads), so
+  // the epilogue rounds it to nearest TF32; tcgen05 would otherwise truncate it (biased towards zero)
+  int round_out = 0;
+  // tensor-core kernel only: x is the RAW pre-BN activation; relu(bn(x)) is applied to the staged operand tiles
+  const BnPrologue* xf = nullptr;
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
 bool conv_tf32_fusable(const ConvArgs& a);   // true when k_conv_fwd_tf32 runs the tensor-core kernel for `a`
+bool conv_tf32_prologue_ok(const ConvArgs& a);   // ... and can take a BnPrologue
 struct WgradArgs {
   const float* x;      // [B,S,S,kpad]
   const float* dy;     // [P,lddy]
   float* dw;           // [taps][npad][kpad]  (+=)
   float* dbias;        // [n] (+=) or null
   int B, S, kpad, n, npad, taps, lddy;
+  // tensor-core kernel only: x is the raw pre-BN activation of the forward conv's input; its boxes are rewritten
+  // to tf32(relu(x * scale + shift)) in shared memory with (mean, rstd, scale, shift)[xf_C] = xf_save
+  const float* xf_save = nullptr;
+  int xf_C = 0;
 };
+bool wgrad_tf32_prologue_ok(const WgradArgs& a);
 int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st);
 int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st);
 

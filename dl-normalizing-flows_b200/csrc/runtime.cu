@@ -137,6 +137,7 @@ struct rnvp_plan {
   int saved_batch = -1;
   int saved_mode = 1;
   int saved_coupling = -1;           // >=0: a stand-alone coupling forward was saved
+  unsigned long long fwd_gen = 0;    // bumped by every forward / inverse call that (over)writes the workspace state
   std::vector<const float*> x_in;    // input of each coupling in the last training forward
 };
 
@@ -285,6 +286,8 @@ int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
   return RNVP_OK;
 }
 
+bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d);
+
 CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
   CplAct a{};
   const int R = p->cfg.res_blocks;
@@ -300,8 +303,8 @@ CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
     for (int i = 0; i < R; ++i) { a.u1[i] = uu; a.u2[i] = uu; }
   }
   a.skip = take(Pn * d.ldD);
-  a.keep_h = mode == 2;
-  if (mode == 2)
+  a.keep_h = mode == 2 && !cpl_xf(p, d);
+  if (a.keep_h)
     for (int i = 0; i < 3 * R + 1; ++i) a.h[i] = take(Pn * d.ldD);
   a.st = take(Pn * d.cst_pad);
   a.xprime = take(Pn * d.cio);
@@ -391,9 +394,36 @@ bool side_stream_enabled() {
   return on != 0;
 }
 
+// BatchNorm2d + ReLU folded into the consuming tensor-core kernels (conv_tc.cu "BN prologue"): on by default,
+// RNVP_XFORM=0 restores the separate bn_relu passes (A/B measurements)
+bool xform_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_XFORM");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+// true when every BN of coupling `d` is applied inside its consumer conv / wgrad kernel (no relu(bn(.)) tensor exists)
+bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d) {
+  if (p->math != RNVP_MATH_TF32 || !xform_enabled()) return false;
+  ConvArgs a{};
+  a.S = d.S; a.kpad = d.ldD; a.ldy = d.ldD; a.n = d.D;
+  WgradArgs w{};
+  w.S = d.S; w.kpad = d.ldD; w.lddy = d.ldD;
+  return conv_tf32_prologue_ok(a) && wgrad_tf32_prologue_ok(w);
+}
+
 int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* stream, Ctx* c) {
   RNVP_REQUIRE(p && p->bound, "plan is not bound to parameters (call rnvp_plan_bind)");
   RNVP_REQUIRE(B > 0, "batch must be positive");
+  if (const int e = dp_sticky_error(&p->dp)) {
+    set_error("data-parallel statistic exchange failed earlier (%s); the replicas have diverged -- rebuild the "
+              "communicator and restore a checkpoint",
+              e == 1 ? "a peer rank never arrived" : (e == 2 ? "the ranks issued different call sequences"
+                                                              : "the ranks' local batch sizes differ"));
+    return RNVP_ERR_STATE;
+  }
   c->p = p; c->B = B; c->mode = mode; c->st = (cudaStream_t)stream;
   c->side_on = mode == 2 && p->side != nullptr && side_stream_enabled() && !g_prof_on;
   c->wst = c->side_on ? p->side : c->st;
@@ -427,7 +457,7 @@ ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x,
 }
 
 int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
-             const float* bias, const float* res, double* stats) {
+             const float* bias, const float* res, double* stats, bool operand_out = false) {
   ProfScope ps(dgrad ? PROF_DGRAD : PROF_CONV, S, cv.taps, dgrad ? cv.cout : cv.cin, dgrad ? cv.cin : cv.cout, c.st);
   ConvArgs a{};
   a.x = x;
@@ -438,7 +468,26 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
   a.n = dgrad ? cv.cin : cv.cout;
   a.npad = dgrad ? cv.npad_b : cv.npad;
   a.taps = cv.taps; a.ldy = ldy;
+  // y is read raw by later conv MMAs: round it where it is produced (tensor-core tier only)
+  a.round_out = operand_out && c.p->math == RNVP_MATH_TF32;
   return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
+}
+// conv whose input is relu(bn_bi(x_raw)): BN prologue inside the tensor-core kernel
+int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, double count, const float* x_raw, int S,
+                float* y, int ldy, const float* bias, const float* res, double* stats, bool operand_out) {
+  rnvp_plan* p = c.p;
+  const CouplingDesc& d = p->cpl[ci];
+  const BnDesc& b = d.bns[bi];
+  ProfScope ps(PROF_CONV, S, cv.taps, cv.cin, cv.cout, c.st);
+  ConvArgs a = conv_args(c, cv, false, x_raw, S, y, ldy, bias, res, stats);
+  a.round_out = operand_out;
+  BnPrologue x{};
+  x.mode = training ? 1 : 0; x.C = b.C; x.sums = c.sf(b.sf); x.count = count;
+  x.gamma = P_<float>(p, d, ci, b.slot_w); x.beta = P_<float>(p, d, ci, b.slot_b);
+  x.run_mean = P_<float>(p, d, ci, b.slot_rm); x.run_var = P_<float>(p, d, ci, b.slot_rv);
+  x.save = c.save(b.save);
+  a.xf = &x;
+  return k_conv_fwd_tf32(a, c.st);
 }
 // the side stream waits for everything enqueued on the main stream so far
 int fork_to_side(const Ctx& c) {
@@ -459,11 +508,14 @@ int join_side(const Ctx& c) {
   return RNVP_OK;
 }
 
-int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy, int lddy, int S, float* dbias) {
+// xf_save != null: x is the raw pre-BN tensor and the kernel applies relu(bn(.)) to its boxes (tensor-core tier)
+int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy, int lddy, int S, float* dbias,
+              const float* xf_save = nullptr, int xf_C = 0) {
   RNVP_TRY(fork_to_side(c));                 // dy (and a recomputed x) were produced on the main stream
   ProfScope ps(PROF_WGRAD, S, cv.taps, cv.cin, cv.cout, c.wst);
   WgradArgs a{};
   a.x = x; a.dy = dy; a.dw = c.dw() + cv.dw_off; a.dbias = dbias;
+  a.xf_save = xf_save; a.xf_C = xf_C;
   a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
   return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.wst) : k_conv_wgrad_fp32(a, c.wst);
 }
@@ -492,6 +544,17 @@ int net_forward(const Ctx& c, int ci, int training) {
   };
   auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
   const ConvDesc* cv = d.convs.data();
+  const bool xf = cpl_xf(p, d);
+  // y = conv(relu(bn_bi(x))): one kernel with the BN prologue, or bn_relu + conv
+  auto bn_conv = [&](int bi, const float* x, const ConvDesc& cvx, float* y, int ldy, const float* b, const float* res,
+                     double* stats, bool operand_out) -> int {
+    if (xf) {
+      if (training) RNVP_TRY(sync_stats(c, c.sf(d.bns[bi].sf), 2 * d.bns[bi].C));
+      return run_conv_bn(c, ci, cvx, bi, training, count, x, S, y, ldy, b, res, stats, operand_out);
+    }
+    RNVP_TRY(bn(bi, x));
+    return run_conv(c, cvx, false, H, S, y, ldy, b, res, stats, operand_out);
+  };
   // The skip path (in_skip and the core_skips, accumulated into `skip`) is off the critical chain of the
   // trunk: with the side stream active (training mode 2, every a_i has its own buffer) those five convs
   // overlap the residual blocks and are joined before out_block's batch norm.
@@ -503,23 +566,19 @@ int net_forward(const Ctx& c, int ci, int training) {
     return run_conv(cs2, cvs, false, x, S, c.act(ci, A.skip), ld, bias(cvs), res, stats);
   };
   // a0 = in_block(h0); skip = in_skip(a0)
-  RNVP_TRY(run_conv(c, cv[0], false, c.act(ci, A.h0), S, c.act(ci, A.a[0]), ld, bias(cv[0]), nullptr, st_of(0)));
+  RNVP_TRY(run_conv(c, cv[0], false, c.act(ci, A.h0), S, c.act(ci, A.a[0]), ld, bias(cv[0]), nullptr, st_of(0), true));
   RNVP_TRY(skip_conv(cv[1], c.act(ci, A.a[0]), nullptr, nullptr));
   for (int i = 0; i < R; ++i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
     float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
-    RNVP_TRY(bn(3 * i, ai));
-    RNVP_TRY(run_conv(c, *rb0, false, H, S, c.act(ci, A.u1[i]), ld, nullptr, nullptr, st_of(3 * i + 1)));
-    RNVP_TRY(bn(3 * i + 1, c.act(ci, A.u1[i])));
-    RNVP_TRY(run_conv(c, *rb3, false, H, S, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2)));
-    RNVP_TRY(bn(3 * i + 2, c.act(ci, A.u2[i])));
-    RNVP_TRY(run_conv(c, *rb6, false, H, S, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr));
+    RNVP_TRY(bn_conv(3 * i, ai, *rb0, c.act(ci, A.u1[i]), ld, nullptr, nullptr, st_of(3 * i + 1), false));
+    RNVP_TRY(bn_conv(3 * i + 1, c.act(ci, A.u1[i]), *rb3, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2), false));
+    RNVP_TRY(bn_conv(3 * i + 2, c.act(ci, A.u2[i]), *rb6, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr, true));
     RNVP_TRY(skip_conv(*cs, an, c.act(ci, A.skip), i == R - 1 ? st_of(3 * R) : nullptr));
   }
   RNVP_TRY(join_side(c));
-  RNVP_TRY(bn(3 * R, c.act(ci, A.skip)));
   const ConvDesc& oc = cv[2 + 4 * R];
-  RNVP_TRY(run_conv(c, oc, false, H, S, c.act(ci, A.st), d.cst_pad, bias(oc), nullptr, nullptr));
+  RNVP_TRY(bn_conv(3 * R, c.act(ci, A.skip), oc, c.act(ci, A.st), d.cst_pad, bias(oc), nullptr, nullptr, false));
   return RNVP_OK;
 }
 
@@ -540,8 +599,16 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   float* Hs = fresh ? nullptr : c.buf(ci, 0);
   float* H = Hs;
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
+  const bool xf = cpl_xf(p, d);
+  // wgrad of a conv whose input was relu(bn_bi(x)): the kernel re-applies the BN to the raw x boxes (tensor-core
+  // tier), else H holds the (kept or recomputed) normalised activation
+  auto wgrad_bn = [&](const ConvDesc& cvw, int bi, const float* x, const float* dy, int lddy, float* dbias) -> int {
+    if (xf) return run_wgrad(c, cvw, x, dy, lddy, S, dbias, c.save(d.bns[bi].save), d.bns[bi].C);
+    return run_wgrad(c, cvw, H, dy, lddy, S, dbias);
+  };
   auto recompute = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
+    if (xf) return RNVP_OK;              // BN prologue: relu(bn(x)) is rebuilt inside the wgrad kernel
     if (A.keep_h) {                      // mode 2: the forward kept relu(bn(x))
       H = c.act(ci, A.h[bi]);
       return RNVP_OK;
@@ -554,8 +621,9 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   // dgrad of `cv` applied to `dy`, then ReLU+BN backward through BN `bi` whose raw input was `x`:
   // g <- masked gradient, out = d(pre-BN input) (+ add).  With the tensor-core tier the mask and the two
   // reductions ride in the dgrad epilogue; otherwise a separate reduce kernel does them.
+  // `operand_out`: `out` is the dy operand of later dgrad / wgrad MMAs (rounded to TF32 by the apply kernel)
   auto dgrad_bn_bwd = [&](const ConvDesc& cvd, const float* dy, int bi, float* g, const float* x, float* out,
-                          const float* add) -> int {
+                          const float* add, bool operand_out) -> int {
     const BnDesc& b = d.bns[bi];
     ConvArgs a = conv_args(c, cvd, true, dy, S, g, ld, nullptr, nullptr, nullptr);
     const bool fused = p->math == RNVP_MATH_TF32 && conv_tf32_fusable(a);
@@ -571,7 +639,7 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
     return k_bn_bwd_apply(g, x, out, add, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
                           P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b),
-                          1.0f / p->world, fused ? 1 : 0, c.st);
+                          1.0f / p->world, fused ? 1 : 0, operand_out && p->math == RNVP_MATH_TF32, c.st);
   };
   const ConvDesc* cv = d.convs.data();
   const ConvDesc& oc = cv[2 + 4 * R];
@@ -580,8 +648,8 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   {
     float* G0 = take(1);
     RNVP_TRY(recompute(3 * R, c.act(ci, A.skip)));
-    RNVP_TRY(run_wgrad(c, oc, H, dst, d.cst_pad, S, gbias(oc)));
-    RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, G0, c.act(ci, A.skip), DO, nullptr));
+    RNVP_TRY(wgrad_bn(oc, 3 * R, c.act(ci, A.skip), dst, d.cst_pad, gbias(oc)));
+    RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, G0, c.act(ci, A.skip), DO, nullptr, true));
   }
   const float* DA = nullptr;               // d(a_{i+1}) accumulated so far
   for (int i = R - 1; i >= 0; --i) {
@@ -591,29 +659,29 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     // skip += core_skip_i(a_{i+1})
     float* DAc = take(3);
     RNVP_TRY(run_wgrad(c, *cs, an, DO, ld, S, gbias(*cs)));
-    RNVP_TRY(run_conv(c, *cs, true, DO, S, DAc, ld, nullptr, DA, nullptr));
+    RNVP_TRY(run_conv(c, *cs, true, DO, S, DAc, ld, nullptr, DA, nullptr, true));
     // a_{i+1} = a_i + rb6(relu(bn3(u2)))
     float* G3 = take(1);
     RNVP_TRY(recompute(3 * i + 2, u2));
-    RNVP_TRY(run_wgrad(c, *rb6, H, DAc, ld, S, gbias(*rb6)));
-    RNVP_TRY(dgrad_bn_bwd(*rb6, DAc, 3 * i + 2, G3, u2, G3, nullptr));
+    RNVP_TRY(wgrad_bn(*rb6, 3 * i + 2, u2, DAc, ld, gbias(*rb6)));
+    RNVP_TRY(dgrad_bn_bwd(*rb6, DAc, 3 * i + 2, G3, u2, G3, nullptr, true));
     // u2 = rb3(relu(bn2(u1)))
     float* G2 = take(2);
     RNVP_TRY(recompute(3 * i + 1, u1));
-    RNVP_TRY(run_wgrad(c, *rb3, H, G3, ld, S, nullptr));
-    RNVP_TRY(dgrad_bn_bwd(*rb3, G3, 3 * i + 1, G2, u1, G2, nullptr));
+    RNVP_TRY(wgrad_bn(*rb3, 3 * i + 1, u1, G3, ld, nullptr));
+    RNVP_TRY(dgrad_bn_bwd(*rb3, G3, 3 * i + 1, G2, u1, G2, nullptr, true));
     // u1 = rb0(relu(bn1(a_i)))
     float* G1 = take(1);
     float* DAn = take(3);
     RNVP_TRY(recompute(3 * i, ai));
-    RNVP_TRY(run_wgrad(c, *rb0, H, G2, ld, S, nullptr));
-    RNVP_TRY(dgrad_bn_bwd(*rb0, G2, 3 * i, G1, ai, DAn, DAc));
+    RNVP_TRY(wgrad_bn(*rb0, 3 * i, ai, G2, ld, nullptr));
+    RNVP_TRY(dgrad_bn_bwd(*rb0, G2, 3 * i, G1, ai, DAn, DAc, false));
     DA = DAn;
   }
   // skip = in_skip(a0) (+...); a0 = in_block(h0)
   float* DAf = take(3);
   RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));
-  RNVP_TRY(run_conv(c, cv[1], true, DO, S, DAf, ld, nullptr, DA, nullptr));
+  RNVP_TRY(run_conv(c, cv[1], true, DO, S, DAf, ld, nullptr, DA, nullptr, true));
   RNVP_TRY(run_wgrad(c, cv[0], c.act(ci, A.h0), DAf, ld, S, gbias(cv[0])));
   RNVP_TRY(run_conv(c, cv[0], true, DAf, S, dh0, d.cin_pad, nullptr, nullptr, nullptr));
   if (fresh) RNVP_REQUIRE(next <= c.L.nbuf, "internal: backward scratch overrun (%d > %d)", next, c.L.nbuf);
@@ -848,6 +916,8 @@ int rnvp_plan_coupling_info(const rnvp_plan* p, int i, char* name, int name_len,
   return RNVP_OK;
 }
 
+unsigned long long rnvp_plan_forward_generation(const rnvp_plan* p) { return p ? p->fwd_gen : 0; }
+
 int rnvp_plan_set_math(rnvp_plan* p, int math) {
   RNVP_REQUIRE(p, "null plan");
   RNVP_REQUIRE(math == RNVP_MATH_FP32 || math == RNVP_MATH_TF32, "unknown math mode %d", math);
@@ -962,7 +1032,9 @@ int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logde
   const int L = cf.num_scales;
   p->saved_batch = -1;
   p->saved_coupling = -1;
+  ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
+  if (training && p->world > 1) RNVP_TRY(dp_check_equal_batches(&p->dp, batch, c.ws_acc() + 8, c.st));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
   if (weight_scale) {
@@ -1083,6 +1155,7 @@ int rnvp_flow_inverse(rnvp_plan* p, const float* z_nchw, float* x_nchw, int batc
   const int L = cf.num_scales;
   p->saved_batch = -1;
   p->saved_coupling = -1;
+  ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
@@ -1134,6 +1207,7 @@ int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nc
   const CouplingDesc& d = p->cpl[ci];
   p->saved_batch = -1;
   p->saved_coupling = -1;
+  ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
@@ -1154,6 +1228,7 @@ int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nc
   const CouplingDesc& d = p->cpl[ci];
   p->saved_batch = -1;
   p->saved_coupling = -1;
+  ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
@@ -1308,6 +1383,51 @@ int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias, i
   a.x = x; a.dy = dy; a.dw = dwf; a.dbias = dbias;
   a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.lddy = lddy;
   return math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, (cudaStream_t)stream) : k_conv_wgrad_fp32(a, (cudaStream_t)stream);
+}
+
+int rnvp_conv_forward_bn(const float* x_raw, const float* wf, const float* bias, const float* res, float* y,
+                         double* stats, int B, int S, int kpad, int n, int npad, int ksize, int ldy, int bn_mode,
+                         int bn_C, const double* bn_sums, double bn_count, const float* gamma, const float* beta,
+                         float* run_mean, float* run_var, float* save, int round_out, void* stream) {
+  ConvArgs a{};
+  a.x = x_raw; a.w = wf; a.bias = bias; a.res = res; a.y = y; a.stats = stats;
+  a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.ldy = ldy;
+  a.round_out = round_out;
+  RNVP_REQUIRE(conv_tf32_prologue_ok(a), "rnvp_conv_forward_bn: shape not supported by the tensor-core kernel");
+  BnPrologue x{bn_mode, bn_C, bn_sums, bn_count, gamma, beta, run_mean, run_var, save};
+  a.xf = &x;
+  return k_conv_fwd_tf32(a, (cudaStream_t)stream);
+}
+int rnvp_conv_wgrad_bn(const float* x_raw, const float* dy, float* dwf, float* dbias, int B, int S, int kpad, int n,
+                       int npad, int ksize, int lddy, const float* bn_save, int bn_C, void* stream) {
+  WgradArgs a{};
+  a.x = x_raw; a.dy = dy; a.dw = dwf; a.dbias = dbias;
+  a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.lddy = lddy;
+  a.xf_save = bn_save; a.xf_C = bn_C;
+  RNVP_REQUIRE(bn_save != nullptr && wgrad_tf32_prologue_ok(a), "rnvp_conv_wgrad_bn: shape not supported by the tensor-core kernel");
+  return k_conv_wgrad_tf32(a, (cudaStream_t)stream);
+}
+
+// ---- batch-norm building blocks (modules_realnvp.py:83-97, 139-143) on [P, ld] NHWC trunk tensors ----------
+int rnvp_bn_relu_forward(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
+                         const float* gamma, const float* beta, float* run_mean, float* run_var, float* save,
+                         int mode, int tf32_round, void* stream) {
+  return k_bn_relu(x, h, P, C, ld, sums, count, gamma, beta, run_mean, run_var, save, mode, tf32_round,
+                   (cudaStream_t)stream);
+}
+int rnvp_conv_dgrad_bn(const float* dy, const float* wb, const float* bn_x, const float* bn_save, float* gm,
+                       double* sums2, int B, int S, int kpad, int n, int npad, int ksize, int ldy, void* stream) {
+  ConvArgs a{};
+  a.x = dy; a.w = wb; a.y = gm; a.stats = sums2; a.bn_x = bn_x; a.bn_save = bn_save;
+  a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.ldy = ldy;
+  RNVP_REQUIRE(conv_tf32_fusable(a), "rnvp_conv_dgrad_bn: shape not supported by the tensor-core kernel");
+  return k_conv_fwd_tf32(a, (cudaStream_t)stream);
+}
+int rnvp_bn_backward_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
+                           const float* save, const double* sums2, double count, const float* gamma, float* dgamma,
+                           float* dbeta, int raw_x_sums, int tf32_round, void* stream) {
+  return k_bn_bwd_apply(gm, x, dx, add, P, C, ld, save, sums2, count, gamma, dgamma, dbeta, 1.0f, raw_x_sums,
+                        tf32_round, (cudaStream_t)stream);
 }
 
 }  // extern "C"

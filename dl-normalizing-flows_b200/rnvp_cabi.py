@@ -49,6 +49,7 @@ def _load():
         "rnvp_plan_bind": (i32, [vp, C.POINTER(vp), C.POINTER(vp), vp]),
         "rnvp_plan_workspace_bytes": (sz, [vp, i32, i32]),
         "rnvp_plan_set_math": (i32, [vp, i32]),
+        "rnvp_plan_forward_generation": (C.c_ulonglong, [vp]),
         "rnvp_flow_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]),
         "rnvp_flow_backward": (i32, [vp, vp, vp, vp, i32, vp, sz, vp]),
         "rnvp_flow_inverse": (i32, [vp, vp, vp, i32, i32, vp, sz, vp]),
@@ -66,6 +67,12 @@ def _load():
         "rnvp_weightnorm_backward": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "rnvp_conv_forward": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
         "rnvp_conv_wgrad": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "rnvp_conv_forward_bn": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, C.c_double,
+                                       vp, vp, vp, vp, vp, i32, vp]),
+        "rnvp_conv_wgrad_bn": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+        "rnvp_bn_relu_forward": (i32, [vp, vp, i32, i32, i32, vp, C.c_double, vp, vp, vp, vp, vp, i32, i32, vp]),
+        "rnvp_conv_dgrad_bn": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
+        "rnvp_bn_backward_apply": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, C.c_double, vp, vp, vp, i32, i32, vp]),
         "rnvp_dp_unique_id": (i32, [vp]),
         "rnvp_dp_init": (i32, [vp, vp, i32, i32]),
         "rnvp_dp_set_grad_layout": (i32, [vp, vp, C.POINTER(C.c_int64), C.c_int64]),

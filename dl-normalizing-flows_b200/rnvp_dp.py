@@ -57,9 +57,16 @@ def broadcast_state(module: nn.Module, group=None) -> None:
             dist.broadcast(t.data, src=src, group=group)
 
 
-def shard_batch(n: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous [begin, end) slice of a global batch of n samples owned by ``rank``."""
+def shard_batch(n: int, rank: int, world: int, drop_last: bool = True) -> Tuple[int, int]:
+    """Contiguous [begin, end) slice of a global batch of n samples owned by ``rank``.
+
+    Synchronised batch norm (count = local pixels x world) and the ncclAvg gradient reduction need EQUAL local
+    batches, so by default the n % world trailing samples are dropped; ``drop_last=False`` hands them out unevenly
+    and is only valid for communication-free work (sampling / evaluation).  Training with unequal shards is
+    detected on the device at the next forward (sticky error 3, ``DataParallel.check_health``)."""
     per, rem = divmod(n, world)
+    if drop_last:
+        return rank * per, rank * per + per
     begin = rank * per + min(rank, rem)
     return begin, begin + per + (1 if rank < rem else 0)
 
@@ -136,12 +143,26 @@ class DataParallel(nn.Module):
         if eng._flat_grad.data_ptr() != self._layout_ptr:
             self._install_layout(eng, self._bucket_elems)
             raise RuntimeError("gradient buffer moved during a step; re-run the step")
+        self.check_health()
+
+    _XCHG_ERRORS = {1: "a peer rank never arrived at a batch-norm statistic exchange",
+                    2: "the ranks issued different sequences of train-mode calls",
+                    3: "the ranks' local batch sizes differ (synchronised batch norm and the gradient average need "
+                       "equal shards: use drop_last / a global batch divisible by the world size)"}
+
+    def check_health(self) -> None:
+        """Raise if the statistic exchange has set its sticky error word (read from mapped host memory: free)."""
+        from rnvp_cabi import lib
+        e = lib.rnvp_dp_xchg_errors(self.module.engine().handle)
+        if e > 0:
+            raise RuntimeError(f"rnvp data parallel: {self._XCHG_ERRORS.get(e, e)}; the replicas have diverged")
 
     def forward(self, x):
         eng = self.module.engine()
         eng.ensure_bound(x.device)
         if eng._flat_grad.data_ptr() != self._layout_ptr:
             self._install_layout(eng, self._bucket_elems)
+        self.check_health()
         return self.module(x)
 
     def log_prob(self, x):

@@ -317,6 +317,7 @@ class FlowLogProb(torch.autograd.Function):
     def forward(ctx, anchor, x, engine: Engine, training: bool):
         ll, _logdet, _z, wsc, ws = engine.flow_forward(x, training, want_z=False, want_ws=True)
         ctx.engine, ctx.ws, ctx.training = engine, ws, training
+        ctx.gen = lib.rnvp_plan_forward_generation(engine.handle)
         ctx.x_meta = x
         ctx.want_dx = ctx.needs_input_grad[1]
         return ll, wsc
@@ -327,6 +328,7 @@ class FlowLogProb(torch.autograd.Function):
             raise RuntimeError("backward through RealNVP needs a train-mode forward (model.train()); "
                                "eval-mode forwards keep no activations")
         eng: Engine = ctx.engine
+        _check_generation(eng, ctx.gen)
         if dll is None:
             dll = torch.zeros(ctx.x_meta.shape[0], dtype=torch.float32, device=ctx.x_meta.device)
         dll = dll.contiguous()
@@ -342,18 +344,31 @@ class CouplingFn(torch.autograd.Function):
     def forward(ctx, anchor, x, engine: Engine, training: bool):
         y, logj, ws = engine.coupling_forward(0, x, training)
         ctx.engine, ctx.ws, ctx.training = engine, ws, training
+        ctx.gen = lib.rnvp_plan_forward_generation(engine.handle)
         return y, logj
 
     @staticmethod
     def backward(ctx, dy, dlogj):
         if not ctx.training:
             raise RuntimeError("backward through a coupling needs a train-mode forward")
+        _check_generation(ctx.engine, ctx.gen)
         if dy is None:
             dy = torch.zeros_like(dlogj)
         if dlogj is None:
             dlogj = torch.zeros_like(dy)
         dx = ctx.engine.coupling_backward(0, dy, dlogj, ctx.ws)
         return None, dx, None, None
+
+
+def _check_generation(engine: Engine, gen: int) -> None:
+    """The activations of a training forward live in the engine's (shared) workspace: a later forward / inverse
+    call of the same module overwrites them, after which the earlier graph can no longer be back-propagated."""
+    now = lib.rnvp_plan_forward_generation(engine.handle)
+    if now != gen:
+        raise RuntimeError(
+            "backward of a stale RealNVP forward: the module ran another forward / inverse pass since this graph "
+            f"was built (generation {gen} -> {now}) and its saved activations were overwritten; call backward() "
+            "before the next forward of the same module")
 
 
 def grad_anchor(device) -> torch.Tensor:

@@ -108,6 +108,11 @@ int rnvp_plan_bind(rnvp_plan* plan, void* const* params_host, void* const* grads
 size_t rnvp_plan_workspace_bytes(const rnvp_plan* plan, int batch, int mode);
 
 int rnvp_plan_set_math(rnvp_plan* plan, int math /* rnvp_math */);
+/* Counter bumped by every rnvp_flow_forward / rnvp_flow_inverse / rnvp_coupling_forward / _inverse call: the
+ * activations a backward call needs live in the caller's workspace and belong to the LAST forward.  A binding that
+ * keeps several forwards alive (autograd) records the value after its forward and refuses a backward whose
+ * record is stale (rnvp_engine.FlowLogProb does).                                                          */
+unsigned long long rnvp_plan_forward_generation(const rnvp_plan* plan);
 
 /* ---- the flow (flow_realnvp.py:196-370) -------------------------------- */
 /* log_prob / forward (flow_realnvp.py:329-340, 354-370).
@@ -196,6 +201,42 @@ int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias,
                     int B, int S, int kpad, int n, int npad, int ksize, int lddy,
                     int math, void* stream);
 
+/* BatchNorm2d -> ReLU -> conv as ONE tensor-core kernel (modules_realnvp.py:83-97, 139-143; tier RNVP_MATH_TF32):
+ *   y = conv(tf32(relu(x_raw * scale + shift)), wf) (+ bias) (+ res), zero padding applied AFTER the activation;
+ * x_raw [B,S,S,kpad] is the raw pre-BN tensor (bn_C real channels), the BN is applied to the operand tiles in
+ * shared memory, so relu(bn(x)) never exists in HBM.  bn_mode / sums / count / gamma / beta / running
+ * statistics / save as in rnvp_bn_relu_forward (mode 1 also saves the coefficients and updates the running
+ * statistics).  round_out: y is rounded to nearest TF32 (it is read raw by another conv MMA).                 */
+int rnvp_conv_forward_bn(const float* x_raw, const float* wf, const float* bias, const float* res, float* y,
+                         double* stats, int B, int S, int kpad, int n, int npad, int ksize, int ldy, int bn_mode,
+                         int bn_C, const double* bn_sums, double bn_count, const float* gamma, const float* beta,
+                         float* run_mean, float* run_var, float* save, int round_out, void* stream);
+/* weight gradient of that conv from the RAW x: dwf[tap][n][k] += sum_p dy[p, n] * tf32(relu(bn(x_raw)))[p + tap, k]
+ * with the coefficients (mean, rstd, scale, shift)[bn_C] the forward saved.                                    */
+int rnvp_conv_wgrad_bn(const float* x_raw, const float* dy, float* dwf, float* dbias, int B, int S, int kpad, int n,
+                       int npad, int ksize, int lddy, const float* bn_save, int bn_C, void* stream);
+
+/* BatchNorm2d + ReLU (modules_realnvp.py:83-85, 139-141) on a [P, ld] NHWC trunk tensor with C real channels:
+ *   mode 1 (training): batch statistics from `sums` (2C doubles: per-channel sum, sum of squares over `count`
+ *           values, as accumulated by a conv epilogue's `stats`); save[4C] = (mean, rstd, scale, shift); running
+ *           statistics updated (momentum 0.1, unbiased variance)
+ *   mode 0 (eval): running statistics;   mode 2: coefficients read back from `save`
+ * tf32_round: h is rounded to nearest TF32 (it is a tensor-core operand).                                   */
+int rnvp_bn_relu_forward(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
+                         const float* gamma, const float* beta, float* run_mean, float* run_var, float* save,
+                         int mode, int tf32_round, void* stream);
+/* The fused backward unit of conv -> BN -> ReLU (autograd of modules_realnvp.py:83-97), tensor-core tier:
+ *   gm[p, n] = (sum_tap sum_k dy[p + tap, k] * wb[tap][n][k]) * 1[bn_x[p, n] * scale[n] + shift[n] > 0]
+ *   sums2[0:n] += sum_p gm,   sums2[n:2n] += sum_p gm * bn_x        (the two BN-backward reductions)
+ * bn_x = the raw pre-BN activations, bn_save = (mean, rstd, scale, shift)[n] of that BN.                     */
+int rnvp_conv_dgrad_bn(const float* dy, const float* wb, const float* bn_x, const float* bn_save, float* gm,
+                       double* sums2, int B, int S, int kpad, int n, int npad, int ksize, int ldy, void* stream);
+/* dx = gamma * rstd * (gm - mean(gm) - xhat * mean(gm * xhat)) (+ add); dgamma / dbeta are added to.
+ * raw_x_sums = 1 when sums2[C:2C] holds sum gm * x (rnvp_conv_dgrad_bn) instead of sum gm * xhat.           */
+int rnvp_bn_backward_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
+                           const float* save, const double* sums2, double count, const float* gamma, float* dgamma,
+                           float* dbeta, int raw_x_sums, int tf32_round, void* stream);
+
 /* ---- data parallel (absent from the reference) ------------- */
 /* 128-byte NCCL unique id, created on rank 0 and shipped by the caller      */
 int rnvp_dp_unique_id(void* id128_host);
@@ -211,7 +252,10 @@ int rnvp_dp_set_grad_layout(rnvp_plan* plan, float* flat, const int64_t* offsets
  * CUDA-IPC handle; after an all-gather of the handles (rank order, world * 64 bytes) rnvp_dp_xchg_open maps
  * the peers' inboxes.  From then on every statistic vector of at most `cap_doubles` is reduced by one
  * single-CTA kernel that pushes it into all inboxes and adds the arrivals up in rank order.
- * rnvp_dp_xchg_errors returns (and clears) the number of exchanges that timed out waiting for a peer.   */
+ * rnvp_dp_xchg_errors returns the exchange's STICKY error word (mapped host memory, no synchronisation): 0 healthy,
+ * 1 a peer never arrived (~2 min), 2 the ranks issued different call sequences, 3 the ranks' local batch sizes
+ * differ (every training forward reduces (B, B^2) first); once set, every compute entry point of the plan fails
+ * with RNVP_ERR_STATE and the affected reductions return NaN.                                            */
 int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64_host);
 int rnvp_dp_xchg_open(rnvp_plan* plan, const void* all_handles_host);
 int rnvp_dp_xchg_errors(rnvp_plan* plan);

@@ -51,6 +51,54 @@ BN_MOMENTUM = 0.1      # nn.BatchNorm2d default
 
 
 # --------------------------------------------------------------------------- #
+# TF32 operand emulation (tests of the tensor-core tier)                      #
+# --------------------------------------------------------------------------- #
+def round_tf32(x: Tensor) -> Tensor:
+    """fp32 -> tf32 (10-bit mantissa) round-to-nearest, ties away from zero == PTX cvt.rna.tf32.f32."""
+    if x.dtype != torch.float32:
+        return x
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _RoundOperand(torch.autograd.Function):
+    """Forward: round to TF32.  Backward: straight through (the rounding is not differentiated)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return round_tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBoth(torch.autograd.Function):
+    """A tensor that is a conv operand in BOTH passes: its value is rounded when it is produced and the
+    gradient arriving at it (summed over all consumers) is rounded before it flows on."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return round_tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return round_tf32(g)
+
+
+class _RoundGrad(torch.autograd.Function):
+    """Identity forward; the gradient w.r.t. this tensor is the ``dy`` operand of a dgrad / wgrad MMA."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return round_tf32(g)
+
+
+# --------------------------------------------------------------------------- #
 # topology                                                                    #
 # --------------------------------------------------------------------------- #
 def coupling_specs(channels: int, image_size: int, base_dim: int, num_scales: int = 5):
@@ -166,7 +214,14 @@ class RealNVPOracle:
 
     def __init__(self, state: Dict[str, Tensor], channels: int, image_size: int,
                  base_dim: int, res_blocks: int, num_scales: int = 5,
-                 prior_loc: float = 0.0, prior_scale: float = 1.0):
+                 prior_loc: float = 0.0, prior_scale: float = 1.0, emulate_tf32: bool = False):
+        # emulate_tf32: restate the arithmetic of the library's tensor-core tier -- every operand of a conv
+        # MMA (activation, weight, and in the backward pass the output gradient) is rounded to TF32 by the
+        # kernel that PRODUCES it (cvt.rna), products are exact, accumulation is fp32; everything that is
+        # not a conv operand stays fp32.  Rounding points (dl-normalizing-flows_b200/csrc):
+        #   forward : w; h0; every relu(bn(.)); the trunk a_i (conv epilogue)
+        #   backward: d st; d skip-sum; d a_i; d u1, d u2 (BN-backward apply / dgrad epilogue outputs)
+        self.emulate_tf32 = emulate_tf32
         self.state = state
         self.channels, self.image_size = channels, image_size
         self.base_dim, self.res_blocks, self.num_scales = base_dim, res_blocks, num_scales
@@ -192,7 +247,19 @@ class RealNVPOracle:
         v, g = self._p(prefix + ".conv.weight_v"), self._p(prefix + ".conv.weight_g")
         w = v * (g / torch.linalg.vector_norm(v, dim=(1, 2, 3), keepdim=True))
         b = self.state.get(prefix + ".conv.bias")
+        if self.emulate_tf32:
+            w = _RoundOperand.apply(w)
         return F.conv2d(x, w, b, stride=1, padding=pad)
+
+    # roles of a tensor under TF32 emulation (identity otherwise)
+    def _act(self, h: Tensor) -> Tensor:          # produced only to be a conv input
+        return _RoundOperand.apply(h) if self.emulate_tf32 else h
+
+    def _trunk(self, a: Tensor) -> Tensor:        # conv input AND carrier of a dy operand
+        return _RoundBoth.apply(a) if self.emulate_tf32 else a
+
+    def _dy(self, t: Tensor) -> Tensor:           # conv output whose gradient is a dy operand
+        return _RoundGrad.apply(t) if self.emulate_tf32 else t
 
     def _bn(self, prefix: str, x: Tensor, affine: bool = True, training: Optional[bool] = None) -> Tensor:
         """nn.BatchNorm2d semantics: batch stats (biased var) in training, running stats in eval."""
@@ -212,24 +279,25 @@ class RealNVPOracle:
     # -- s/t network ------------------------------------------------------- #
     def _res_block(self, prefix: str, x: Tensor) -> Tensor:
         """Bottleneck block (modules_realnvp.py:83-97,114)."""
-        h = F.relu(self._bn(prefix + ".in_block.0", x))
-        h = self._rec(prefix + ".u1", self._wn_conv(prefix + ".res_block.0", h, 0))
-        h = F.relu(self._bn(prefix + ".res_block.1", h))
-        h = self._rec(prefix + ".u2", self._wn_conv(prefix + ".res_block.3", h, 1))
-        h = F.relu(self._bn(prefix + ".res_block.4", h))
+        h = self._act(F.relu(self._bn(prefix + ".in_block.0", x)))
+        h = self._rec(prefix + ".u1", self._dy(self._wn_conv(prefix + ".res_block.0", h, 0)))
+        h = self._act(F.relu(self._bn(prefix + ".res_block.1", h)))
+        h = self._rec(prefix + ".u2", self._dy(self._wn_conv(prefix + ".res_block.3", h, 1)))
+        h = self._act(F.relu(self._bn(prefix + ".res_block.4", h)))
         h = self._wn_conv(prefix + ".res_block.6", h, 0)
-        return x + h
+        return self._trunk(x + h)
 
     def _res_module(self, prefix: str, x: Tensor) -> Tensor:
         """ResidualModule with skip connections (modules_realnvp.py:175-194)."""
-        a = self._rec(prefix + ".a0", self._wn_conv(prefix + ".in_block", x, 1))
+        a = self._rec(prefix + ".a0", self._trunk(self._wn_conv(prefix + ".in_block", self._act(x), 1)))
         out = self._wn_conv(prefix + ".in_skip", a, 0)
         for i in range(self.res_blocks):
             a = self._rec(f"{prefix}.a{i + 1}", self._res_block(f"{prefix}.core_block.{i}", a))
             out = out + self._wn_conv(f"{prefix}.core_skips.{i}", a, 0)
+        out = self._dy(out)
         self._rec(prefix + ".skipsum", out)
-        h = F.relu(self._bn(prefix + ".out_block.0", out))
-        return self._rec(prefix + ".st", self._wn_conv(prefix + ".out_block.2", h, 0))
+        h = self._act(F.relu(self._bn(prefix + ".out_block.0", out)))
+        return self._rec(prefix + ".st", self._dy(self._wn_conv(prefix + ".out_block.2", h, 0)))
 
     # -- couplings --------------------------------------------------------- #
     def coupling(self, name: str, x: Tensor, reverse: bool = False,

@@ -64,15 +64,18 @@ def _host_logic(rank, world):
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     assert all(torch.equal(g, gathered[0]) for g in gathered)
-    # sharding covers the batch exactly once
-    sl = [rnvp_dp.shard_batch(11, r, world) for r in range(world)]
+    # uneven sharding (communication-free work only) covers the batch exactly once
+    sl = [rnvp_dp.shard_batch(11, r, world, drop_last=False) for r in range(world)]
     assert sl[0][0] == 0 and sl[-1][1] == 11 and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
-    return rnvp_dp.shard_batch(11, rank, world)
+    # the training default: equal shards, the n % world trailing samples are dropped
+    eq = [rnvp_dp.shard_batch(11, r, world) for r in range(world)]
+    assert len({b - a for a, b in eq}) == 1 and eq[-1][1] == 10 and all(a[1] == b[0] for a, b in zip(eq, eq[1:]))
+    return rnvp_dp.shard_batch(11, rank, world, drop_last=False), rnvp_dp.shard_batch(11, rank, world)
 
 
 def test_dp_host_logic_gloo():
     out = _run(_host_logic)
-    assert out == [(0, 6), (6, 11)]
+    assert out == [((0, 6), (0, 5)), ((6, 11), (5, 10))]
 
 
 def test_bucket_planning():

@@ -121,6 +121,28 @@ def test_gradient_accumulation_and_zero_grad(pkg, golden_dir):
     assert not torch.equal(dict(m.named_parameters())[k].detach().cpu(), st0[k])
 
 
+def test_stale_backward_is_rejected(pkg, golden_dir):
+    """The activations of a train-mode forward live in the engine's workspace: a second forward of the same module
+    overwrites them, and back-propagating the FIRST graph afterwards must raise instead of silently producing
+    gradients from the wrong activations (same batch size, so the batch guard alone would not notice)."""
+    fix = torch.load(os.path.join(golden_dir, "tiny_32px_b4.pt"))
+    c = fix["config"]
+    st0 = O.random_state(c["channels"], c["image"], c["base_dim"], c["res_blocks"], c["num_scales"], seed=c["seed"])
+    m = build(pkg, c, st0, "fp32")
+    m.train()
+    x = fix["x"].to(DEV)
+    ll1, ws1 = m(x)
+    ll2, ws2 = m(x * 0.5)
+    with pytest.raises(RuntimeError, match="stale"):
+        ll1.sum().backward()
+    ll2.sum().backward()                       # the latest graph is fine
+    ll3, _ = m(x)
+    with torch.no_grad():
+        m.g(torch.randn_like(x))               # an inverse pass reuses the inference workspace, not the saved tensors...
+    with pytest.raises(RuntimeError, match="stale"):
+        ll3.sum().backward()                   # ...but it re-materialises the weights: treated as stale, conservatively
+
+
 def test_input_gradient(pkg, golden_dir):
     """dLoss/dx from rnvp_flow_backward vs autograd through the oracle."""
     c = dict(channels=3, image=16, base_dim=4, res_blocks=1, num_scales=3, B=3)

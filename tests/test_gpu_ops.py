@@ -168,20 +168,144 @@ def test_conv_tf32(pkg, shape):
     _conv_case(pkg, B, S, cin, cout, k, 1, seed=1, with_res=False)
 
 
-HALO_SHAPES = [(2, 64, 32, 32, 3), (2, 32, 64, 64, 3), (2, 16, 128, 128, 3), (3, 16, 25, 128, 3), (2, 64, 7, 32, 3),
-               (1, 32, 13, 64, 3)]
+def _nhwc(t, ld):
+    """(B,C,S,S) -> zero-padded NHWC [B,S,S,ld] on the device."""
+    B, Cc, S, _ = t.shape
+    out = torch.zeros(B, S, S, ld)
+    out[..., :Cc] = t.permute(0, 2, 3, 1)
+    return out.to(DEV)
 
 
-def test_conv_tf32_halo():
-    """The opt-in 3x3 halo path (RNVP_HALO=1, read once per process): one haloed activation tile per 32-channel
-    chunk, the nine taps through row-shifted shared-memory descriptors; streamed and resident weight tiles."""
-    import os
-    import subprocess
-    import sys
-    code = ("import sys, importlib; sys.path[:0] = [%r, %r]; import conftest; "
-            "pkg = importlib.import_module('dl-normalizing-flows_b200'); import test_gpu_ops as T; "
-            "[T._conv_case(pkg, *s, 1) for s in T.HALO_SHAPES]; print('halo ok')"
-            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-    env = dict(os.environ, RNVP_HALO="1")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "halo ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+def _wn_operands(pkg, v, gg):
+    lib, check, ptr = pkg.rnvp_cabi.lib, pkg.rnvp_cabi.check, pkg.rnvp_cabi.ptr
+    cout, cin, k, _ = v.shape
+    kpad, npad, kpad_b, npad_b = _pad(cin, 32), _pad(cout, 16), _pad(cout, 32), _pad(cin, 16)
+    arena = torch.empty(k * k * npad * kpad + k * k * npad_b * kpad_b, device=DEV)
+    wf, wb = arena[: k * k * npad * kpad], arena[k * k * npad * kpad:]
+    check(lib.rnvp_weightnorm_forward(ptr(v.to(DEV)), ptr(gg.to(DEV)), ptr(wf), ptr(wb), cout, cin, k, _stream()))
+    return wf, wb
+
+
+BN_SHAPES = [(2, 64, 32, 32, 1), (2, 64, 32, 32, 3), (3, 32, 64, 64, 3), (2, 16, 128, 128, 1), (2, 16, 128, 24, 1),
+             (5, 8, 256, 256, 3), (37, 4, 512, 512, 1), (9, 4, 512, 96, 1), (3, 8, 12, 32, 3), (1, 32, 64, 64, 1)]
+
+
+@pytest.mark.parametrize("shape", BN_SHAPES)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_conv_bn_prologue(pkg, shape, mode):
+    """BatchNorm2d -> ReLU -> conv in ONE tcgen05 kernel (the BN is applied to the staged operand tiles) against
+    torch's three ops (modules_realnvp.py:83-97).  beta is shifted up so that relu(bn(0)) != 0: zero padding
+    must be applied AFTER the activation.  Also pins the saved coefficients, the running-statistic update and the
+    wgrad that rebuilds relu(bn(x)) from the raw x boxes."""
+    lib, check, ptr = pkg.rnvp_cabi.lib, pkg.rnvp_cabi.check, pkg.rnvp_cabi.ptr
+    B, S, cin, cout, k = shape
+    g = torch.Generator().manual_seed(B * 1000 + S + cin + cout + k)
+    x = torch.randn(B, cin, S, S, generator=g) * 1.5 + 0.3
+    v = torch.randn(cout, cin, k, k, generator=g)
+    gg = torch.rand(cout, 1, 1, 1, generator=g) + 0.5
+    w = v * (gg / torch.linalg.vector_norm(v, dim=(1, 2, 3), keepdim=True))
+    gamma, beta = torch.rand(cin, generator=g) + 0.5, torch.rand(cin, generator=g) * 0.6
+    rm0, rv0 = torch.randn(cin, generator=g) * 0.1 + 0.3, torch.rand(cin, generator=g) + 1.5
+    bias, res = torch.randn(cout, generator=g), torch.randn(B, cout, S, S, generator=g)
+    bn = torch.nn.BatchNorm2d(cin)
+    with torch.no_grad():
+        bn.weight.copy_(gamma); bn.bias.copy_(beta); bn.running_mean.copy_(rm0); bn.running_var.copy_(rv0)
+    bn.train(mode == "train")
+    h_ref = F.relu(bn(x)).detach()
+    y_ref = F.conv2d(h_ref, w, bias, padding=k // 2) + res
+    kpad, npad, ldy = _pad(cin, 32), _pad(cout, 16), _pad(cout, 32)
+    wf, _wb = _wn_operands(pkg, v, gg)
+    xn = _nhwc(x, kpad)
+    y = _nhwc(res, ldy)
+    P = B * S * S
+    sums = torch.cat((x.double().sum((0, 2, 3)), (x.double() ** 2).sum((0, 2, 3)))).to(DEV)
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    rm, rv, save = rm0.to(DEV), rv0.to(DEV), torch.zeros(4 * cin, device=DEV)
+    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias.to(DEV)), ptr(y), ptr(y), ptr(stats), B, S, kpad, cout, npad,
+                                   k, ldy, 1 if mode == "train" else 0, cin, ptr(sums), float(P), ptr(gamma.to(DEV)),
+                                   ptr(beta.to(DEV)), ptr(rm), ptr(rv), ptr(save), 0, _stream()))
+    got = y[..., :cout].permute(0, 3, 1, 2).cpu()
+    assert rel(got, y_ref) < 3e-3, (rel(got, y_ref), shape, mode)
+    s_ref = torch.cat((y_ref.double().sum((0, 2, 3)), (y_ref.double() ** 2).sum((0, 2, 3))))
+    assert rel(stats, s_ref) < 3e-3
+    if mode == "eval":
+        assert torch.equal(rm.cpu(), rm0) and torch.equal(rv.cpu(), rv0)
+        return
+    assert torch.allclose(rm.cpu(), bn.running_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rv.cpu(), bn.running_var, rtol=1e-5, atol=1e-6)
+    mean, var = x.mean((0, 2, 3)), x.var((0, 2, 3), unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    sv = save.cpu().view(4, cin)
+    assert rel(sv[0], mean) < 1e-5 and rel(sv[1], rstd) < 1e-5
+    assert rel(sv[2], gamma * rstd) < 1e-5 and rel(sv[3], beta - mean * gamma * rstd) < 1e-5
+    # the same tile transform with the coefficients read back (mode 2) reproduces the result bit for bit
+    y2 = _nhwc(res, ldy)
+    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias.to(DEV)), ptr(y2), ptr(y2), None, B, S, kpad, cout, npad,
+                                   k, ldy, 2, cin, None, float(P), None, None, None, None, ptr(save), 0, _stream()))
+    assert torch.equal(y2, y)
+    # weight gradient from the RAW x boxes
+    dy = torch.randn(B, cout, S, S, generator=g)
+    dw_ref = torch.nn.grad.conv2d_weight(h_ref, w.shape, dy, padding=k // 2)
+    dyn = _nhwc(dy, _pad(cout, 32))
+    dwf = torch.zeros(k * k, npad, kpad, device=DEV)
+    db = torch.zeros(cout, device=DEV)
+    check(lib.rnvp_conv_wgrad_bn(ptr(xn), ptr(dyn), ptr(dwf), ptr(db), B, S, kpad, cout, npad, k, _pad(cout, 32),
+                                 ptr(save), cin, _stream()))
+    got_dw = dwf[:, :cout, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1).cpu()
+    assert rel(got_dw, dw_ref) < 3e-3, (rel(got_dw, dw_ref), shape)
+    assert rel(db, dy.sum((0, 2, 3))) < 2e-3
+    assert float(dwf[:, cout:, :].abs().max() if npad > cout else 0) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 32, 32, 1), (2, 32, 64, 64, 3), (3, 16, 128, 128, 3), (5, 8, 256, 256, 1),
+                                   (21, 4, 512, 512, 3), (2, 16, 24, 128, 1), (3, 8, 96, 256, 1)])
+def test_dgrad_bn_relu_fused(pkg, shape):
+    """The backward unit of x -> BN(train) -> ReLU -> conv: dgrad with the ReLU mask and the two BN-backward
+    reductions in its epilogue (rnvp_conv_dgrad_bn), then rnvp_bn_backward_apply -- against torch autograd through
+    the three reference ops (modules_realnvp.py:83-97), incl. dgamma / dbeta and the residual-gradient add."""
+    lib, check, ptr = pkg.rnvp_cabi.lib, pkg.rnvp_cabi.check, pkg.rnvp_cabi.ptr
+    B, S, cout, cin, k = shape                 # conv: cin -> cout; the BN under test normalises its cin-channel INPUT
+    g = torch.Generator().manual_seed(7 + B + S + cin + cout + k)
+    x = (torch.randn(B, cin, S, S, generator=g) * 1.3 + 0.2).requires_grad_(True)
+    v = torch.randn(cout, cin, k, k, generator=g)
+    gg = torch.rand(cout, 1, 1, 1, generator=g) + 0.5
+    w = v * (gg / torch.linalg.vector_norm(v, dim=(1, 2, 3), keepdim=True))
+    gamma = (torch.rand(cin, generator=g) + 0.5).requires_grad_(True)
+    beta = (torch.rand(cin, generator=g) * 0.4 - 0.2).requires_grad_(True)
+    dy = torch.randn(B, cout, S, S, generator=g)
+    add = torch.randn(B, cin, S, S, generator=g)
+    h = F.relu(F.batch_norm(x, None, None, gamma, beta, True, 0.1, 1e-5))
+    (F.conv2d(h, w, None, padding=k // 2) * dy).sum().backward()
+    P = B * S * S
+    xd = x.detach()
+    mean, var = xd.mean((0, 2, 3)), xd.var((0, 2, 3), unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    gd, bd = gamma.detach(), beta.detach()
+    save = torch.cat((mean, rstd, gd * rstd, bd - mean * gd * rstd)).to(DEV)
+    _wf, wb = _wn_operands(pkg, v, gg)
+    ld = _pad(cin, 32)
+    xn, dyn = _nhwc(xd, ld), _nhwc(dy, _pad(cout, 32))
+    gm = torch.zeros(B, S, S, ld, device=DEV)
+    sums2 = torch.zeros(2 * cin, dtype=torch.float64, device=DEV)
+    check(lib.rnvp_conv_dgrad_bn(ptr(dyn), ptr(wb), ptr(xn), ptr(save), ptr(gm), ptr(sums2), B, S, _pad(cout, 32), cin,
+                                 _pad(cin, 16), k, ld, _stream()))
+    dh_ref = torch.nn.grad.conv2d_input(xd.shape, w, dy, padding=k // 2) * (h.detach() > 0)
+    assert rel(gm[..., :cin].permute(0, 3, 1, 2), dh_ref) < 3e-3
+    s_ref = torch.cat((dh_ref.double().sum((0, 2, 3)), (dh_ref.double() * xd.double()).sum((0, 2, 3))))
+    assert rel(sums2[:cin], s_ref[:cin]) < 3e-3 and rel(sums2[cin:], s_ref[cin:]) < 3e-3
+    dx = torch.zeros_like(gm)
+    dgam, dbet = torch.zeros(cin, device=DEV), torch.zeros(cin, device=DEV)
+    addn = _nhwc(add, ld)
+    check(lib.rnvp_bn_backward_apply(ptr(gm), ptr(xn), ptr(dx), ptr(addn), P, cin, ld, ptr(save), ptr(sums2), float(P),
+                                     ptr(gd.to(DEV)), ptr(dgam), ptr(dbet), 1, 0, _stream()))
+    got = dx[..., :cin].permute(0, 3, 1, 2).cpu() - add
+    assert rel(got, x.grad) < 5e-3, (rel(got, x.grad), shape)
+    assert rel(dgam, gamma.grad) < 5e-3 and rel(dbet, beta.grad) < 5e-3
+    if ld > cin:
+        assert float(dx[..., cin:].abs().max()) == 0.0
+    # the rounded variant only differs by the TF32 rounding of its output
+    dxr = torch.zeros_like(gm)
+    dgam.zero_(); dbet.zero_()
+    check(lib.rnvp_bn_backward_apply(ptr(gm), ptr(xn), ptr(dxr), ptr(addn), P, cin, ld, ptr(save), ptr(sums2), float(P),
+                                     ptr(gd.to(DEV)), ptr(dgam), ptr(dbet), 1, 1, _stream()))
+    assert torch.equal(dxr.cpu(), O.round_tf32(dx.cpu()))

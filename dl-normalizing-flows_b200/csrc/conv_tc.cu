@@ -143,6 +143,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor (sm_100 version 1), 128-byte swizzle
 //   K-major : 8-row x 128B atoms stacked every SBO bytes; LBO unused
 //   MN-major: 32 MN-elements x 8 K-rows atoms; next 32 MN-elements at LBO, next 8 K-rows at SBO
@@ -211,7 +222,9 @@ constexpr int XF_MAX_K = 512;            // input channels (padded) the BN prolo
 // of the column chunks) so that twice as many residual prefetches / result stores are in flight, and a
 // three-deep ring to pay for their staging buffers.  The narrower tiles keep four warps (two CTAs per SM).
 template <int BN, int XF> struct TcCfg {
-  static constexpr int STAGES = XF ? (BN == 128 ? 4 : 3) : (BN == 32 ? 3 : (BN == 64 ? 2 : 3));
+  // ring depth cap (the launch takes as many stages as keep MIN_CTAS resident).  The BN prologue adds a pipeline step
+  // (TMA -> transform -> MMA), so those kernels want one stage more in flight.
+  static constexpr int STAGES = XF ? (BN == 128 ? 5 : (BN == 64 ? 4 : 5)) : 3;
   static constexpr int EPI_WARPS = BN == 128 ? 8 : 4;
   static constexpr int XF_WARPS = XF ? 4 : 0;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * XF_WARPS;
@@ -240,6 +253,8 @@ struct ConvTcParams {
   float* xf_rm;
   float* xf_rv;
   float* xf_save;                    // [4C] mean, rstd, scale, shift
+  // coupling epilogue (CPL kernels: the s/t net's out conv, n_tiles == 1)
+  CplEpilogue cpl;
 };
 
 // byte offset of logical 16-byte chunk j of row r inside a 128B-swizzled box
@@ -278,7 +293,7 @@ __device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* 
   }
 }
 
-template <int BN, int XF>
+template <int BN, int XF, int CPL>
 __global__ void __launch_bounds__(TcCfg<BN, XF>::THREADS, TcCfg<BN, XF>::MIN_CTAS)
 conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
@@ -326,6 +341,9 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     for (int s = 0; s < EW; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
+  }
+  if constexpr (CPL) {
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) { red_sum[0][i] = 0.f; red_sq[0][i] = 0.f; }
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(&tmem_base_slot);
   // everything above overlaps the tail of the previous kernel; from here on its results are needed.
@@ -504,12 +522,86 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const bool pvalid = prow0 + lane < prm.P;
       mbar_wait(&acc_full[as], (ti >> 1) & 1);
       tc_fence_after();
+      if constexpr (CPL) {
+        // ---- the coupling itself, on the accumulator of the s/t net's out conv (modules_realnvp.py:277-301,
+        // 339-361): lane = pixel; columns [0,cio) hold t, [cio,2cio) hold l.  s = (scale*tanh(l)+shift)*(1-m),
+        // t *= (1-m); forward x' = x*exp(s)+t, inverse x = (y_unbn - t)*exp(-s); per-sample log-det by shuffles.
+        const CplEpilogue& cp = prm.cpl;
+        const CplGeom& g = cp.g;
+        const int p = prow0 + lane;
+        const bool ok = p < prm.P;
+        const float keep = (ok && g.ckbd) ? (float)(1 - ((g.cfg + (p & (prm.S - 1)) + ((p >> prm.log2S) & (prm.S - 1))) & 1))
+                                          : (ok ? 1.f : 0.f);
+        const float scale = *cp.scale, sshift = *cp.sshift;
+        constexpr int NH = EW / 4;                       // epilogue warps sharing a TMEM lane quarter split the channels
+        const int cper = (ceil_div(g.cio, NH) + 7) & ~7;
+        const int c_lo = (ew >> 2) * cper, c_hi = min(g.cio, c_lo + cper);
+        float ssum = 0.f;
+        for (int cb = c_lo; cb < c_hi; cb += 8) {
+          float tv[8], lv[8];
+          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+          tmem_ld_32x8(tb + (uint32_t)cb, tv);
+          tmem_ld_32x8(tb + (uint32_t)(g.cio + cb), lv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int c = cb + j;
+            const bool cv = c < c_hi;                    // uniform across the warp
+            float outv = 0.f, s = 0.f;
+            if (cv && ok) {
+              const float t = (tv[j] + prm.bias[c]) * keep;
+              const float l = lv[j] + prm.bias[g.cio + c];
+              s = (scale * tanhf(l) + sshift) * keep;
+              const float xin = cp.x[(int64_t)p * g.C + g.on_off + c];
+              if (cp.mode == 3) {                        // reverse=True: un-BN with the RUNNING statistics, then invert
+                const float hl = 0.5f * logf(cp.run_var[c] + 1e-5f);
+                const float xt = xin * expf(hl * keep) + cp.run_mean[c] * keep;
+                outv = (xt - t) * expf(-s);
+                cp.out[(int64_t)p * g.C + g.on_off + c] = outv;
+                if (!g.ckbd) cp.out[(int64_t)p * g.C + g.in_off + c] = cp.x[(int64_t)p * g.C + g.in_off + c];
+              } else {
+                const float xp = xin * expf(s) + t;
+                outv = xp;
+                if (cp.mode == 1) {                      // training: x' now, out_bn needs its batch statistics first
+                  cp.out[(int64_t)p * g.cio + c] = xp;
+                  ssum += s;
+                } else {                                 // eval: out_bn with the running statistics right here
+                  const float rv = cp.run_var[c];
+                  const float hl = 0.5f * logf(rv + 1e-5f);
+                  const float yn = (xp - cp.run_mean[c]) * (1.0f / sqrtf(rv + kBnEps));
+                  cp.out[(int64_t)p * g.C + g.on_off + c] = keep != 0.f ? yn : xp;
+                  if (!g.ckbd) cp.out[(int64_t)p * g.C + g.in_off + c] = cp.x[(int64_t)p * g.C + g.in_off + c];
+                  const float lj = s - hl * keep;
+                  ssum += lj;
+                  if (cp.logJ) {
+                    cp.logJ[(int64_t)p * g.C + g.on_off + c] = lj;
+                    if (!g.ckbd) cp.logJ[(int64_t)p * g.C + g.in_off + c] = 0.f;
+                  }
+                }
+              }
+            }
+            if (cp.mode == 1 && cv) {                    // batch statistics of x' for out_bn (all positions)
+              const float a1 = warp_sum(outv), a2 = warp_sum(outv * outv);
+              if (lane == 0) { atomicAdd(&red_sum[0][c], a1); atomicAdd(&red_sq[0][c], a2); }
+            }
+          }
+        }
+        if (cp.mode != 3) {
+          // per-sample log-det: the 32 pixels of a warp belong to one sample (hw >= 32) or to 32 / hw samples
+          const int hw = prm.S * prm.S;
+          const int width = hw < 32 ? hw : 32;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+            if (o < width) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+          if ((lane & (width - 1)) == 0 && ok) atomicAdd(&cp.logdet_acc[p >> (2 * prm.log2S)], (double)ssum);
+        }
+      }
+      const bool store_st = !CPL || prm.cpl.store_st;
 #pragma unroll
       for (int cl = 0; cl < CH_PER_WARP; ++cl) {
         const int ci = ci_lo + cl;
         const int c0 = ci * 32;
         const int nb = n0 + c0;
-        if (ci >= chunks_per_tile || nb >= prm.n) break;
+        if (!store_st || ci >= chunks_per_tile || nb >= prm.n) break;
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
         if (prm.bias) {
@@ -642,6 +734,16 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
     }
     if (lane == 0) tma_store_wait_all();
+    if constexpr (CPL) {
+      if (prm.cpl.mode == 1) {
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+        const int cio = prm.cpl.g.cio;
+        for (int c = threadIdx.x - 64; c < cio; c += 32 * EW) {
+          atomicAdd(&prm.cpl.sums[c], (double)red_sum[0][c]);
+          atomicAdd(&prm.cpl.sums[cio + c], (double)red_sq[0][c]);
+        }
+      }
+    } else
     if (keep_stats && own_ntile) {
       // every warp publishes a full row of BN partial sums (zero outside its own chunks)
       for (int c = lane; c < BN; c += 32) { red_sum[ew][c] = 0.f; red_sq[ew][c] = 0.f; }
@@ -750,7 +852,7 @@ struct FwdKernelInfo {
   int max_stages = 0, by_regs = 0, static_smem = 0;
   int status = RNVP_OK;
 };
-template <int BN, int XF>
+template <int BN, int XF, int CPL>
 static const FwdKernelInfo& fwd_kernel_info() {
   static const FwdKernelInfo info = [] {
     FwdKernelInfo k;
@@ -759,12 +861,12 @@ static const FwdKernelInfo& fwd_kernel_info() {
                           : (BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
     k.max_stages = env_int(name, 1, TC_MAX_STAGES, TcCfg<BN, XF>::STAGES);
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN, XF>) != cudaSuccess) { k.status = RNVP_ERR_CUDA; return k; }
+    if (cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN, XF, CPL>) != cudaSuccess) { k.status = RNVP_ERR_CUDA; return k; }
     k.by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
     k.static_smem = (int)fa.sharedSizeBytes;
-    if (cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024 - k.static_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared) != cudaSuccess)
       k.status = RNVP_ERR_CUDA;
     return k;
@@ -772,7 +874,7 @@ static const FwdKernelInfo& fwd_kernel_info() {
   return info;
 }
 
-template <int BN, int XF>
+template <int BN, int XF, int CPL = 0>
 static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmY, tmR;
   int bw = 0, bh = 0, bn = 0;
@@ -787,7 +889,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   if (rsrc) RNVP_TRY(make_row_map(&tmR, rsrc, prm.P, a.n, a.ldy));
   else tmR = tmY;
   constexpr int THREADS = TcCfg<BN, XF>::THREADS;
-  const FwdKernelInfo& ki = fwd_kernel_info<BN, XF>();
+  const FwdKernelInfo& ki = fwd_kernel_info<BN, XF, CPL>();
   RNVP_REQUIRE(ki.status == RNVP_OK, "conv: cudaFuncGetAttributes / cudaFuncSetAttribute failed");
   // shared-memory plan: epilogue staging (a residual box only when the layer has one; one output box per warp
   // for the 32-wide tile, whose warps stage one box per tile) + as many ring stages as keep MIN_CTAS resident
@@ -822,7 +924,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas;
   if (grid > tiles) grid = tiles;
-  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN, XF>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
+  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN, XF, CPL>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -865,10 +967,19 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
     RNVP_REQUIRE(x.mode != 1 || (x.sums && x.save), "BN prologue: training mode needs sums and save");
     prm.xf_mode = x.mode; prm.xf_C = x.C; prm.xf_sums = x.sums; prm.xf_count = x.count;
     prm.xf_gamma = x.gamma; prm.xf_beta = x.beta; prm.xf_rm = x.run_mean; prm.xf_rv = x.run_var; prm.xf_save = x.save;
+    if (a.cpl && a.cpl->mode) {
+      RNVP_REQUIRE(a.n <= 128 && a.bias && !a.res && a.n == 2 * a.cpl->g.cio,
+                   "coupling epilogue: the out conv must have a bias, no residual and 2*cio <= 128 outputs");
+      prm.cpl = *a.cpl;
+      if (a.n <= 32) return launch_fwd<32, 1, 1>(a, prm, st);
+      if (a.n <= 64) return launch_fwd<64, 1, 1>(a, prm, st);
+      return launch_fwd<128, 1, 1>(a, prm, st);
+    }
     if (a.n <= 32) return launch_fwd<32, 1>(a, prm, st);
     if (a.n <= 64) return launch_fwd<64, 1>(a, prm, st);
     return launch_fwd<128, 1>(a, prm, st);
   }
+  RNVP_REQUIRE(a.cpl == nullptr || a.cpl->mode == 0, "the coupling epilogue rides on the BN-prologue kernel");
   if (a.n <= 32) return launch_fwd<32, 0>(a, prm, st);
   if (a.n <= 64) return launch_fwd<64, 0>(a, prm, st);
   return launch_fwd<128, 0>(a, prm, st);
@@ -1230,7 +1341,11 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   } else {
     prm.a_stage_bytes = 4 * WG_BOX_BYTES;           // full 4-box slots: trailing groups read idle smem
     prm.a_lbo = WG_BOX_BYTES;
-    if (variant != 0 && prm.tmem_cols <= 256 && 2 * prm.a_stage_bytes + 2 * prm.b_stage_bytes <= 100 * 1024) {
+    // BN prologue: the transform is one more pipeline step; RNVP_WG_XF_DEEP=1 trades the second CTA per SM for a
+    // four-deep A ring on those launches (A/B switch)
+    static const int xf_deep = env_int("RNVP_WG_XF_DEEP", 0, 1, 0);
+    if (variant != 0 && !(a.xf_save && xf_deep) && prm.tmem_cols <= 256 &&
+        2 * prm.a_stage_bytes + 2 * prm.b_stage_bytes <= 100 * 1024) {
       prm.a_stages = 2;                             // two CTAs per SM hide the per-tile latency better
       prm.b_stages = (100 * 1024 - 2 * prm.a_stage_bytes) / prm.b_stage_bytes;
       if (prm.b_stages > 4) prm.b_stages = 4;

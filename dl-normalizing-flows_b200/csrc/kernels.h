@@ -153,6 +153,26 @@ struct BnPrologue {
   float* run_var;
   float* save;         // [4C] mean, rstd, scale, shift: written in mode 1, read in mode 2
 };
+// The affine coupling fused into the epilogue of the s/t network's out conv (modules_realnvp.py:277-301, 339-361):
+// the accumulator row of a pixel holds (t | l); the epilogue forms s = (scale*tanh(l)+shift)*(1-m), t*(1-m) and
+//   mode 1 (training forward): x' = x*exp(s)+t -> out [P,cio]; sums += (sum x', sum x'^2); logdet_acc[b] += sum s
+//   mode 2 (eval forward)    : y = out_bn_running(x') (masked) -> out [P,C]; logdet_acc[b] += sum (s - hl*(1-m))
+//   mode 3 (reverse=True)    : x = (y*exp(hl*(1-m)) + rm*(1-m) - t)*exp(-s) -> out [P,C]
+// with hl = 0.5*log(running_var + 1e-5).  The per-sample log-det is reduced with warp shuffles.
+struct CplEpilogue {
+  int mode = 0;
+  int store_st = 0;            // also write the raw (t | l) tensor (the backward pass reads l)
+  CplGeom g;
+  const float* x = nullptr;    // coupling input (forward) / output (reverse), NHWC [P,C]
+  float* out = nullptr;
+  float* logJ = nullptr;       // mode 2: optional full log_diag_J tensor [P,C]
+  const float* scale = nullptr;
+  const float* sshift = nullptr;
+  const float* run_mean = nullptr;   // out_bn running statistics (modes 2, 3)
+  const float* run_var = nullptr;
+  double* sums = nullptr;      // mode 1: [2 cio]
+  double* logdet_acc = nullptr;
+};
 struct ConvArgs {
   const float* x;      // [B,S,S,kpad] activated input
   const float* w;      // [taps][npad][kpad]
@@ -170,6 +190,7 @@ struct ConvArgs {
   int round_out = 0;
   // tensor-core kernel only: x is the RAW pre-BN activation; relu(bn(x)) is applied to the staged operand tiles
   const BnPrologue* xf = nullptr;
+  const CplEpilogue* cpl = nullptr;          // with xf only: the out conv of a coupling's s/t network
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);

@@ -287,6 +287,7 @@ int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
 }
 
 bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d);
+bool bn_fused(const rnvp_plan* p, const CouplingDesc& d, int bi);
 
 CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
   CplAct a{};
@@ -303,9 +304,11 @@ CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
     for (int i = 0; i < R; ++i) { a.u1[i] = uu; a.u2[i] = uu; }
   }
   a.skip = take(Pn * d.ldD);
-  a.keep_h = mode == 2 && !cpl_xf(p, d);
+  // mode 2 keeps relu(bn(.)) for the backward -- except where the BN is applied inside its consumer kernels
+  a.keep_h = mode == 2;
   if (a.keep_h)
-    for (int i = 0; i < 3 * R + 1; ++i) a.h[i] = take(Pn * d.ldD);
+    for (int i = 0; i < 3 * R + 1; ++i)
+      if (!bn_fused(p, d, i)) a.h[i] = take(Pn * d.ldD);
   a.st = take(Pn * d.cst_pad);
   a.xprime = take(Pn * d.cio);
   a.y = take(Pn * d.C);
@@ -404,7 +407,7 @@ bool xform_enabled() {
   }
   return on != 0;
 }
-// true when every BN of coupling `d` is applied inside its consumer conv / wgrad kernel (no relu(bn(.)) tensor exists)
+// true when the tensor-core kernels of coupling `d` can apply a BN to their operand tiles (shape / tier check)
 bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d) {
   if (p->math != RNVP_MATH_TF32 || !xform_enabled()) return false;
   ConvArgs a{};
@@ -412,6 +415,27 @@ bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d) {
   WgradArgs w{};
   w.S = d.S; w.kpad = d.ldD; w.lddy = d.ldD;
   return conv_tf32_prologue_ok(a) && wgrad_tf32_prologue_ok(w);
+}
+
+// BN `bi` of the s/t net ([bn1, bn2, bn3] x R, out_block.0) is folded into its consumer conv and that conv's wgrad,
+// i.e. relu(bn(.)) never exists in HBM.  Only the 1x1 consumers (rb0 after bn1, rb6 after bn3, the out conv) take
+// the fold: a 3x3 conv would re-transform every activation tile for each of its nine taps -- measured 2x slower than
+// one bn_relu pass + the plain kernel (profiles/r02a_*), its operand feed being shared-memory-bandwidth bound.
+bool bn_fused(const rnvp_plan* p, const CouplingDesc& d, int bi) {
+  const int R = p->cfg.res_blocks;
+  const bool consumer_1x1 = bi == 3 * R || bi % 3 != 1;
+  return consumer_1x1 && cpl_xf(p, d);
+}
+
+// the affine coupling map computed in the epilogue of the s/t net's out conv (needs the BN-prologue kernel);
+// RNVP_CPL_EPILOGUE=0 restores the separate cpl_fwd_a / cpl_inv passes (A/B measurements)
+bool cpl_fused(const rnvp_plan* p, const CouplingDesc& d) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_CPL_EPILOGUE");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0 && cpl_xf(p, d) && d.cst <= 128;
 }
 
 int make_ctx(rnvp_plan* p, int B, int mode, void* ws, size_t ws_bytes, void* stream, Ctx* c) {
@@ -474,7 +498,8 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
 }
 // conv whose input is relu(bn_bi(x_raw)): BN prologue inside the tensor-core kernel
 int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, double count, const float* x_raw, int S,
-                float* y, int ldy, const float* bias, const float* res, double* stats, bool operand_out) {
+                float* y, int ldy, const float* bias, const float* res, double* stats, bool operand_out,
+                const CplEpilogue* cpl = nullptr) {
   rnvp_plan* p = c.p;
   const CouplingDesc& d = p->cpl[ci];
   const BnDesc& b = d.bns[bi];
@@ -487,6 +512,7 @@ int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, 
   x.run_mean = P_<float>(p, d, ci, b.slot_rm); x.run_var = P_<float>(p, d, ci, b.slot_rv);
   x.save = c.save(b.save);
   a.xf = &x;
+  a.cpl = cpl;
   return k_conv_fwd_tf32(a, c.st);
 }
 // the side stream waits for everything enqueued on the main stream so far
@@ -523,7 +549,8 @@ int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy,
 // ------------------------------------------------------------------------------------
 // s/t network (ResidualModule, modules_realnvp.py:175-194) forward
 // ------------------------------------------------------------------------------------
-int net_forward(const Ctx& c, int ci, int training) {
+// `cpl` (tensor-core tier only): the coupling map fused into the out conv's epilogue
+int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nullptr) {
   rnvp_plan* p = c.p;
   const CouplingDesc& d = p->cpl[ci];
   const int R = p->cfg.res_blocks, S = d.S, ld = d.ldD, Pn = c.B * S * S;
@@ -544,11 +571,11 @@ int net_forward(const Ctx& c, int ci, int training) {
   };
   auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
   const ConvDesc* cv = d.convs.data();
-  const bool xf = cpl_xf(p, d);
+  const bool xf = bn_fused(p, d, 3 * R);
   // y = conv(relu(bn_bi(x))): one kernel with the BN prologue, or bn_relu + conv
   auto bn_conv = [&](int bi, const float* x, const ConvDesc& cvx, float* y, int ldy, const float* b, const float* res,
                      double* stats, bool operand_out) -> int {
-    if (xf) {
+    if (bn_fused(p, d, bi)) {
       if (training) RNVP_TRY(sync_stats(c, c.sf(d.bns[bi].sf), 2 * d.bns[bi].C));
       return run_conv_bn(c, ci, cvx, bi, training, count, x, S, y, ldy, b, res, stats, operand_out);
     }
@@ -578,6 +605,12 @@ int net_forward(const Ctx& c, int ci, int training) {
   }
   RNVP_TRY(join_side(c));
   const ConvDesc& oc = cv[2 + 4 * R];
+  if (cpl) {
+    RNVP_REQUIRE(xf, "internal: coupling epilogue without the BN-prologue kernel");
+    if (training) RNVP_TRY(sync_stats(c, c.sf(d.bns[3 * R].sf), 2 * d.bns[3 * R].C));
+    return run_conv_bn(c, ci, oc, 3 * R, training, count, c.act(ci, A.skip), S, c.act(ci, A.st), d.cst_pad, bias(oc),
+                       nullptr, nullptr, false, cpl);
+  }
   RNVP_TRY(bn_conv(3 * R, c.act(ci, A.skip), oc, c.act(ci, A.st), d.cst_pad, bias(oc), nullptr, nullptr, false));
   return RNVP_OK;
 }
@@ -599,16 +632,15 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   float* Hs = fresh ? nullptr : c.buf(ci, 0);
   float* H = Hs;
   auto gbias = [&](const ConvDesc& cv) { return cv.has_bias ? G_(p, ci, cv.slot_bias) : nullptr; };
-  const bool xf = cpl_xf(p, d);
-  // wgrad of a conv whose input was relu(bn_bi(x)): the kernel re-applies the BN to the raw x boxes (tensor-core
-  // tier), else H holds the (kept or recomputed) normalised activation
+  // wgrad of a conv whose input was relu(bn_bi(x)): the kernel re-applies the BN to the raw x boxes (folded BNs),
+  // else H holds the (kept or recomputed) normalised activation
   auto wgrad_bn = [&](const ConvDesc& cvw, int bi, const float* x, const float* dy, int lddy, float* dbias) -> int {
-    if (xf) return run_wgrad(c, cvw, x, dy, lddy, S, dbias, c.save(d.bns[bi].save), d.bns[bi].C);
+    if (bn_fused(p, d, bi)) return run_wgrad(c, cvw, x, dy, lddy, S, dbias, c.save(d.bns[bi].save), d.bns[bi].C);
     return run_wgrad(c, cvw, H, dy, lddy, S, dbias);
   };
   auto recompute = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
-    if (xf) return RNVP_OK;              // BN prologue: relu(bn(x)) is rebuilt inside the wgrad kernel
+    if (bn_fused(p, d, bi)) return RNVP_OK;   // relu(bn(x)) is rebuilt inside the wgrad kernel
     if (A.keep_h) {                      // mode 2: the forward kept relu(bn(x))
       H = c.act(ci, A.h[bi]);
       return RNVP_OK;
@@ -705,9 +737,25 @@ int coupling_forward(const Ctx& c, int ci, const float* x, float* y, float* logJ
                           P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
                           P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0),
                           p->math == RNVP_MATH_TF32, c.st));
-  RNVP_TRY(net_forward(c, ci, training));
-  RNVP_TRY(k_cpl_fwd_a(x, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT),
-                       c.act(ci, A.xprime), c.sf(d.sf_out), c.logdet_acc(), training, c.st));
+  if (cpl_fused(p, d)) {
+    // the affine map rides in the out conv's epilogue: training leaves x' + its batch statistics for out_bn (one
+    // more tiny pass below); eval finishes the coupling there
+    CplEpilogue e{};
+    e.mode = training ? 1 : 2;
+    e.store_st = training ? 1 : 0;
+    e.g = g; e.x = x;
+    e.out = training ? c.act(ci, A.xprime) : y;
+    e.logJ = training ? nullptr : logJ;
+    e.scale = P_<float>(p, d, ci, SLOT_SCALE); e.sshift = P_<float>(p, d, ci, SLOT_SSHIFT);
+    e.run_mean = P_<float>(p, d, ci, SLOT_OUTBN_RM); e.run_var = P_<float>(p, d, ci, SLOT_OUTBN_RV);
+    e.sums = c.sf(d.sf_out); e.logdet_acc = c.logdet_acc();
+    RNVP_TRY(net_forward(c, ci, training, &e));
+    if (!training) return RNVP_OK;
+  } else {
+    RNVP_TRY(net_forward(c, ci, training));
+    RNVP_TRY(k_cpl_fwd_a(x, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT),
+                         c.act(ci, A.xprime), c.sf(d.sf_out), c.logdet_acc(), training, c.st));
+  }
   if (training) RNVP_TRY(sync_stats(c, c.sf(d.sf_out), 2 * d.cio));
   RNVP_TRY(k_cpl_fwd_b(c.act(ci, A.xprime), x, c.act(ci, A.st), g, c.sf(d.sf_out), count,
                        P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
@@ -731,6 +779,14 @@ int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int trainin
                           P_<float>(p, d, ci, SLOT_INBN_B), P_<float>(p, d, ci, SLOT_INBN_RM),
                           P_<float>(p, d, ci, SLOT_INBN_RV), c.save(d.save_in), training, c.act(ci, A.h0),
                           p->math == RNVP_MATH_TF32, c.st));
+  if (cpl_fused(p, d)) {
+    CplEpilogue e{};
+    e.mode = 3;
+    e.g = g; e.x = y; e.out = x;
+    e.scale = P_<float>(p, d, ci, SLOT_SCALE); e.sshift = P_<float>(p, d, ci, SLOT_SSHIFT);
+    e.run_mean = P_<float>(p, d, ci, SLOT_OUTBN_RM); e.run_var = P_<float>(p, d, ci, SLOT_OUTBN_RV);
+    return net_forward(c, ci, training, &e);
+  }
   RNVP_TRY(net_forward(c, ci, training));
   RNVP_TRY(k_cpl_inv(y, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
                      P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), x, c.st));

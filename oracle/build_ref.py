@@ -1,7 +1,7 @@
 """Build oracle/_ref/ from the UNMODIFIED reference under /root/reference  --  TEST / BASELINE INFRASTRUCTURE.
 
 The reference is pure Python, so "building" it means byte-compiling the three modules of the hot path
-(flow_realnvp.py, modules_realnvp.py, utils.py) where they lie into sourceless ``.pyc`` files under
+(flow_realnvp.py, modules_realnvp.py, utils.py) where they lie into sourceless byte-code files (``<module>.bin``: the snapshot that ships the repo to the GPU box skips ``*.pyc``) under
 ``oracle/_ref/``.  No reference source is copied into the repository: ``oracle/_ref/`` is git-ignored, holds
 build outputs only and travels to the GPU box with the snapshot, exactly like the repo's own ``.so`` files.  There
 ``bench.py --impl reference`` / ``cpu_baseline`` / ``gpu_eager_baseline`` import it (``oracle/ref_loader.py``) and
@@ -26,7 +26,7 @@ def build() -> bool:
     os.makedirs(OUT, exist_ok=True)
     for m in MODULES:
         # dfile: the path recorded in tracebacks stays the reference's own
-        py_compile.compile(os.path.join(REF, m + ".py"), cfile=os.path.join(OUT, m + ".pyc"),
+        py_compile.compile(os.path.join(REF, m + ".py"), cfile=os.path.join(OUT, m + ".bin"),
                            dfile=f"reference/{m}.py", doraise=True, optimize=0)
     with open(os.path.join(OUT, "BUILD_INFO"), "w") as f:
         f.write(f"byte-compiled from {REF} by oracle/build_ref.py with python {sys.version.split()[0]}\n")

@@ -20,7 +20,7 @@ _ORIG_CUDA = None
 
 
 def available() -> bool:
-    return all(os.path.exists(os.path.join(REF_DIR, m + ".pyc")) for m in ("flow_realnvp", "modules_realnvp", "utils"))
+    return all(os.path.exists(os.path.join(REF_DIR, m + ".bin")) for m in ("flow_realnvp", "modules_realnvp", "utils"))
 
 
 def load(cpu: bool = True):
@@ -42,7 +42,7 @@ def load(cpu: bool = True):
     mods = {}
     try:
         for name in ("utils", "modules_realnvp", "flow_realnvp"):       # import order = dependency order
-            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_DIR, name + ".pyc"))
+            loader = importlib.machinery.SourcelessFileLoader(name, os.path.join(REF_DIR, name + ".bin"))
             spec = importlib.util.spec_from_loader(name, loader)
             mod = importlib.util.module_from_spec(spec)
             sys.modules[name] = mod          # the reference modules import each other by these names

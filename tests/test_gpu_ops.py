@@ -111,7 +111,8 @@ def _conv_case(pkg, B, S, cin, cout, k, math, seed=0, with_res=True):
     resn[..., :cout] = res.permute(0, 2, 3, 1)
     y = resn.to(DEV).clone()
     stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
-    check(lib.rnvp_conv_forward(ptr(xn), ptr(wf), ptr(bias.to(DEV)), ptr(y) if with_res else None, ptr(y), ptr(stats),
+    bias_d = bias.to(DEV)
+    check(lib.rnvp_conv_forward(ptr(xn), ptr(wf), ptr(bias_d), ptr(y) if with_res else None, ptr(y), ptr(stats),
                                 B, S, kpad, cout, npad, k, ldy, math, _stream()))
     got = y[..., :cout].permute(0, 3, 1, 2).cpu()
     tol = 1e-5 if math == 0 else 3e-3
@@ -221,9 +222,10 @@ def test_conv_bn_prologue(pkg, shape, mode):
     sums = torch.cat((x.double().sum((0, 2, 3)), (x.double() ** 2).sum((0, 2, 3)))).to(DEV)
     stats = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
     rm, rv, save = rm0.to(DEV), rv0.to(DEV), torch.zeros(4 * cin, device=DEV)
-    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias.to(DEV)), ptr(y), ptr(y), ptr(stats), B, S, kpad, cout, npad,
-                                   k, ldy, 1 if mode == "train" else 0, cin, ptr(sums), float(P), ptr(gamma.to(DEV)),
-                                   ptr(beta.to(DEV)), ptr(rm), ptr(rv), ptr(save), 0, _stream()))
+    bias_d, gamma_d, beta_d = bias.to(DEV), gamma.to(DEV), beta.to(DEV)      # named: the pointers must stay valid
+    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias_d), ptr(y), ptr(y), ptr(stats), B, S, kpad, cout, npad,
+                                   k, ldy, 1 if mode == "train" else 0, cin, ptr(sums), float(P), ptr(gamma_d),
+                                   ptr(beta_d), ptr(rm), ptr(rv), ptr(save), 0, _stream()))
     got = y[..., :cout].permute(0, 3, 1, 2).cpu()
     assert rel(got, y_ref) < 3e-3, (rel(got, y_ref), shape, mode)
     s_ref = torch.cat((y_ref.double().sum((0, 2, 3)), (y_ref.double() ** 2).sum((0, 2, 3))))
@@ -240,7 +242,7 @@ def test_conv_bn_prologue(pkg, shape, mode):
     assert rel(sv[2], gamma * rstd) < 1e-5 and rel(sv[3], beta - mean * gamma * rstd) < 1e-5
     # the same tile transform with the coefficients read back (mode 2) reproduces the result bit for bit
     y2 = _nhwc(res, ldy)
-    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias.to(DEV)), ptr(y2), ptr(y2), None, B, S, kpad, cout, npad,
+    check(lib.rnvp_conv_forward_bn(ptr(xn), ptr(wf), ptr(bias_d), ptr(y2), ptr(y2), None, B, S, kpad, cout, npad,
                                    k, ldy, 2, cin, None, float(P), None, None, None, None, ptr(save), 0, _stream()))
     assert torch.equal(y2, y)
     # weight gradient from the RAW x boxes
@@ -289,17 +291,26 @@ def test_dgrad_bn_relu_fused(pkg, shape):
     sums2 = torch.zeros(2 * cin, dtype=torch.float64, device=DEV)
     check(lib.rnvp_conv_dgrad_bn(ptr(dyn), ptr(wb), ptr(xn), ptr(save), ptr(gm), ptr(sums2), B, S, _pad(cout, 32), cin,
                                  _pad(cin, 16), k, ld, _stream()))
+    # The kernel takes the ReLU mask from fma(x, scale, shift) > 0, torch from its own BN formula: an activation within
+    # ~1e-6 of the threshold may be masked differently (an O(1) difference on that one element).  Such elements are
+    # excluded from the pointwise comparison and bounded in number.
+    pre = (xd - mean.view(1, -1, 1, 1)) * (gd * rstd).view(1, -1, 1, 1) + bd.view(1, -1, 1, 1)
+    sure = pre.abs() > 1e-5
+    assert int((~sure).sum()) <= 8
     dh_ref = torch.nn.grad.conv2d_input(xd.shape, w, dy, padding=k // 2) * (h.detach() > 0)
-    assert rel(gm[..., :cin].permute(0, 3, 1, 2), dh_ref) < 3e-3
+    gm_c = gm[..., :cin].permute(0, 3, 1, 2).cpu()
+    assert rel(gm_c * sure, dh_ref * sure) < 3e-3
     s_ref = torch.cat((dh_ref.double().sum((0, 2, 3)), (dh_ref.double() * xd.double()).sum((0, 2, 3))))
-    assert rel(sums2[:cin], s_ref[:cin]) < 3e-3 and rel(sums2[cin:], s_ref[cin:]) < 3e-3
+    scale_s = float(dh_ref.double().abs().sum((0, 2, 3)).max())          # sums of signed values: compare on the L1 scale
+    assert float((sums2.cpu() - s_ref).abs().max()) < 3e-3 * scale_s
     dx = torch.zeros_like(gm)
     dgam, dbet = torch.zeros(cin, device=DEV), torch.zeros(cin, device=DEV)
     addn = _nhwc(add, ld)
+    gd_d = gd.to(DEV)
     check(lib.rnvp_bn_backward_apply(ptr(gm), ptr(xn), ptr(dx), ptr(addn), P, cin, ld, ptr(save), ptr(sums2), float(P),
-                                     ptr(gd.to(DEV)), ptr(dgam), ptr(dbet), 1, 0, _stream()))
+                                     ptr(gd_d), ptr(dgam), ptr(dbet), 1, 0, _stream()))
     got = dx[..., :cin].permute(0, 3, 1, 2).cpu() - add
-    assert rel(got, x.grad) < 5e-3, (rel(got, x.grad), shape)
+    assert rel(got * sure, x.grad * sure) < 5e-3, (rel(got * sure, x.grad * sure), shape)
     assert rel(dgam, gamma.grad) < 5e-3 and rel(dbet, beta.grad) < 5e-3
     if ld > cin:
         assert float(dx[..., cin:].abs().max()) == 0.0
@@ -307,5 +318,5 @@ def test_dgrad_bn_relu_fused(pkg, shape):
     dxr = torch.zeros_like(gm)
     dgam.zero_(); dbet.zero_()
     check(lib.rnvp_bn_backward_apply(ptr(gm), ptr(xn), ptr(dxr), ptr(addn), P, cin, ld, ptr(save), ptr(sums2), float(P),
-                                     ptr(gd.to(DEV)), ptr(dgam), ptr(dbet), 1, 1, _stream()))
+                                     ptr(gd_d), ptr(dgam), ptr(dbet), 1, 1, _stream()))
     assert torch.equal(dxr.cpu(), O.round_tf32(dx.cpu()))

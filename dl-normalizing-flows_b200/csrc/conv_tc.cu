@@ -558,6 +558,10 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 outv = (xt - t) * expf(-s);
                 cp.out[(int64_t)p * g.C + g.on_off + c] = outv;
                 if (!g.ckbd) cp.out[(int64_t)p * g.C + g.in_off + c] = cp.x[(int64_t)p * g.C + g.in_off + c];
+                if (cp.logJ) {                           // the reference returns log_rescale here (:283, :302)
+                  cp.logJ[(int64_t)p * g.C + g.on_off + c] = s;
+                  if (!g.ckbd) cp.logJ[(int64_t)p * g.C + g.in_off + c] = 0.f;
+                }
               } else {
                 const float xp = xin * expf(s) + t;
                 outv = xp;

@@ -725,7 +725,7 @@ int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g
 __global__ void cpl_inv_kernel(const float* __restrict__ y, const float* __restrict__ stt, CplGeom g,
                                const float* __restrict__ run_mean, const float* __restrict__ run_var,
                                const float* __restrict__ scale_p, const float* __restrict__ sshift_p,
-                               float* __restrict__ x) {
+                               float* __restrict__ x, float* __restrict__ logJ) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_mean[kMaxCio], s_hl[kMaxCio];
@@ -748,14 +748,18 @@ __global__ void cpl_inv_kernel(const float* __restrict__ y, const float* __restr
       float s = (scale * tanhf(l) + sshift) * keep;
       x[(int64_t)p * g.C + g.on_off + c] = (xt - t) * expf(-s);
       if (!g.ckbd) x[(int64_t)p * g.C + g.in_off + c] = y[(int64_t)p * g.C + g.in_off + c];
+      if (logJ) {                                  // the reference returns log_rescale (modules_realnvp.py:283, 302)
+        logJ[(int64_t)p * g.C + g.on_off + c] = s;
+        if (!g.ckbd) logJ[(int64_t)p * g.C + g.in_off + c] = 0.f;
+      }
     }
   }
 }
 int k_cpl_inv(const float* y, const float* stt, CplGeom g, const float* run_mean, const float* run_var,
-              const float* scale, const float* sshift, float* x, cudaStream_t st) {
+              const float* scale, const float* sshift, float* x, float* logJ, cudaStream_t st) {
   if (g.P() == 0) return RNVP_OK;
   RNVP_CUDA(launch_pdl(cpl_inv_kernel, cpl_grid(g.P(), kThreads, g.cio, kNumSMs * 8), dim3(kThreads), 0, st, y, stt, g, run_mean, run_var,
-                                                                                      scale, sshift, x));
+                                                                                      scale, sshift, x, logJ));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

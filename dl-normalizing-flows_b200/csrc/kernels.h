@@ -59,7 +59,7 @@ int k_cpl_fwd_b(const float* xprime, const float* x, const float* stt, CplGeom g
                 const float* scale, const float* sshift, float* y, float* logJ, double* logdet_acc,
                 cudaStream_t st);
 int k_cpl_inv(const float* y, const float* stt, CplGeom g, const float* run_mean, const float* run_var,
-              const float* scale, const float* sshift, float* x, cudaStream_t st);
+              const float* scale, const float* sshift, float* x, float* logJ, cudaStream_t st);
 // sums2: [0:cio] sum g, [cio:2cio] sum g*xhat, [2cio] K = sum_p dll_b(p)*keep_p
 int k_cpl_bwd_a(const float* dy, const float* xprime, CplGeom g, const float* save, const float* dll,
                 double* sums2, cudaStream_t st);
@@ -165,7 +165,7 @@ struct CplEpilogue {
   CplGeom g;
   const float* x = nullptr;    // coupling input (forward) / output (reverse), NHWC [P,C]
   float* out = nullptr;
-  float* logJ = nullptr;       // mode 2: optional full log_diag_J tensor [P,C]
+  float* logJ = nullptr;       // modes 2, 3: optional full log_diag_J tensor [P,C] (mode 3: log_rescale)
   const float* scale = nullptr;
   const float* sshift = nullptr;
   const float* run_mean = nullptr;   // out_bn running statistics (modes 2, 3)

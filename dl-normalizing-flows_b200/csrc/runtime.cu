@@ -765,7 +765,7 @@ int coupling_forward(const Ctx& c, int ci, const float* x, float* y, float* logJ
   return RNVP_OK;
 }
 
-int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int training) {
+int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int training, float* logJ = nullptr) {
   rnvp_plan* p = c.p;
   const CouplingDesc& d = p->cpl[ci];
   CplGeom g = d.geom(c.B);
@@ -782,14 +782,14 @@ int coupling_inverse(const Ctx& c, int ci, const float* y, float* x, int trainin
   if (cpl_fused(p, d)) {
     CplEpilogue e{};
     e.mode = 3;
-    e.g = g; e.x = y; e.out = x;
+    e.g = g; e.x = y; e.out = x; e.logJ = logJ;
     e.scale = P_<float>(p, d, ci, SLOT_SCALE); e.sshift = P_<float>(p, d, ci, SLOT_SSHIFT);
     e.run_mean = P_<float>(p, d, ci, SLOT_OUTBN_RM); e.run_var = P_<float>(p, d, ci, SLOT_OUTBN_RV);
     return net_forward(c, ci, training, &e);
   }
   RNVP_TRY(net_forward(c, ci, training));
   RNVP_TRY(k_cpl_inv(y, c.act(ci, A.st), g, P_<float>(p, d, ci, SLOT_OUTBN_RM), P_<float>(p, d, ci, SLOT_OUTBN_RV),
-                     P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), x, c.st));
+                     P_<float>(p, d, ci, SLOT_SCALE), P_<float>(p, d, ci, SLOT_SSHIFT), x, logJ, c.st));
   return RNVP_OK;
 }
 
@@ -1276,8 +1276,8 @@ int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nc
   return RNVP_OK;
 }
 
-int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nchw, int batch, int training,
-                          void* ws, size_t ws_bytes, void* stream) {
+int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nchw, float* logJ_nchw, int batch,
+                          int training, void* ws, size_t ws_bytes, void* stream) {
   Ctx c;
   RNVP_TRY(make_ctx(p, batch, 0, ws, ws_bytes, stream, &c));
   RNVP_REQUIRE(ci >= 0 && ci < (int)p->cpl.size(), "coupling index %d out of range", ci);
@@ -1290,8 +1290,9 @@ int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nc
   RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
   FlowBufs f = flow_bufs(c);
   RNVP_TRY(k_nchw_to_nhwc(y_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
-  RNVP_TRY(coupling_inverse(c, ci, f.T[0], f.T[1], training));
+  RNVP_TRY(coupling_inverse(c, ci, f.T[0], f.T[1], training, logJ_nchw ? f.G[0] : nullptr));
   RNVP_TRY(k_nhwc_to_nchw(f.T[1], x_nchw, batch, d.C, d.S, d.S, c.st));
+  if (logJ_nchw) RNVP_TRY(k_nhwc_to_nchw(f.G[0], logJ_nchw, batch, d.C, d.S, d.S, c.st));
   return RNVP_OK;
 }
 

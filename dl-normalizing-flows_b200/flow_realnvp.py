@@ -22,7 +22,34 @@ import torch.nn as nn
 
 import rnvp_engine as _eng
 from rnvp_cabi import check, lib, ptr
-from modules_realnvp import ChannelwiseAffineCoupling, CheckerboardAffineCoupling
+from modules_realnvp import ChannelwiseAffineCoupling, CheckerboardAffineCoupling, _native_hps
+
+_FACTOR_TAPS = ((0, 0), (1, 1), (0, 1), (1, 0))        # k -> (dy, dx) of factor_out (flow_realnvp.py:148-164)
+
+
+# ATen forms of the layout maps (differentiable): used by the hyper-parameter branches that run on torch operators
+def _t_squeeze(x):
+    B, Cc, H, W = x.shape
+    return x.reshape(B, Cc, H // 2, 2, W // 2, 2).permute(0, 1, 3, 5, 2, 4).reshape(B, Cc * 4, H // 2, W // 2)
+
+
+def _t_undo_squeeze(x):
+    B, Cc, H, W = x.shape
+    return x.reshape(B, Cc // 4, 2, 2, H, W).permute(0, 1, 4, 2, 5, 3).reshape(B, Cc // 4, H * 2, W * 2)
+
+
+def _t_factor_out(x):
+    full = torch.cat([x[:, :, dy::2, dx::2] for dy, dx in _FACTOR_TAPS], dim=1)
+    return full.chunk(2, dim=1)
+
+
+def _t_restore(on, off):
+    full = torch.cat((on, off), dim=1)
+    B, C4, H, W = full.shape
+    out = full.new_zeros(B, C4 // 4, H * 2, W * 2)
+    for k, (dy, dx) in enumerate(_FACTOR_TAPS):
+        out[:, :, dy::2, dx::2] = full[:, k * (C4 // 4):(k + 1) * (C4 // 4)]
+    return out
 
 
 def _stream(t):
@@ -38,6 +65,9 @@ class RealNVP(nn.Module):
         self.num_scales = num_scales
         self._hps = hps
         self._engine = None
+        # the configuration train.py constructs runs on the sm_100a kernels; the other hyper-parameter branches
+        #  compose the modules' ATen forwards on the device
+        self._native = _native_hps(hps)
         if image_size % (1 << (num_scales - 1)):
             raise ValueError(f"image_size={image_size} must be divisible by 2^{num_scales - 1}")
         chan, size, dim = channels, image_size, hps.base_dim
@@ -86,6 +116,8 @@ class RealNVP(nn.Module):
     def set_math(self, mode: str) -> None:
         """'tf32' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core fp32, 1e-5 parity tier)."""
         import rnvp_cabi
+        if not self._native:
+            return
         self.engine().set_math({"fp32": rnvp_cabi.MATH_FP32, "tf32": rnvp_cabi.MATH_TF32}[mode])
         for cpl in self._couplings():
             cpl.set_math(mode)
@@ -136,8 +168,24 @@ class RealNVP(nn.Module):
     # -- z -> x and x -> z ------------------------------------------------------------------ #
     def g(self, z):
         """Inverse pass (flow_realnvp.py:196-249): one fused call, no autograd."""
+        if not self._native:
+            return self._aten_g(z)
         with torch.no_grad():
             return self.engine().flow_inverse(z, self.training)
+
+    def _aten_g(self, z):
+        x, offs = z, []
+        for _ in range(1, self.num_scales):
+            x, off = _t_factor_out(x)
+            offs.append(off)
+        for s, kind, group in reversed(list(self._groups())):
+            if s < self.num_scales and kind == "chan":
+                x = _t_squeeze(_t_restore(x, offs[s - 1]))
+            for cpl in reversed(group):
+                x, _ = cpl(x, reverse=True)
+            if kind == "chan":
+                x = _t_undo_squeeze(x)
+        return x
 
     def f(self, x):
         """x -> (z, log_diag_J) with the full Jacobian-diagonal tensor (flow_realnvp.py:252-327).
@@ -145,22 +193,24 @@ class RealNVP(nn.Module):
         API-parity path: runs coupling by coupling so that log_diag_J can be carried through the
         squeeze / factor_out permutations like the reference does.  ``log_prob`` does not use it.
         """
+        sq, usq, fo, rs = ((self.squeeze, self.undo_squeeze, self.factor_out, self.restore) if self._native else
+                           (_t_squeeze, _t_undo_squeeze, _t_factor_out, _t_restore))
         z, J = x, torch.zeros_like(x)
         z_off, J_off = [], []
         for s, kind, group in self._groups():
             if kind == "chan":
-                z, J = self.squeeze(z), self.squeeze(J)
+                z, J = sq(z), sq(J)
             for cpl in group:
                 z, inc = cpl(z)
                 J = J + inc
             if kind == "chan":
-                z, J = self.undo_squeeze(z), self.undo_squeeze(J)
-                z, zo = self.factor_out(z)
-                J, Jo = self.factor_out(J)
+                z, J = usq(z), usq(J)
+                z, zo = fo(z)
+                J, Jo = fo(J)
                 z_off.append(zo)
                 J_off.append(Jo)
         for zo, Jo in zip(reversed(z_off), reversed(J_off)):
-            z, J = self.restore(z, zo), self.restore(J, Jo)
+            z, J = rs(z, zo), rs(J, Jo)
         return z, J
 
     def log_prob(self, x):
@@ -168,6 +218,16 @@ class RealNVP(nn.Module):
         return self._log_prob_ws(x)[0]
 
     def _log_prob_ws(self, x):
+        if not self._native:
+            if not x.is_cuda:
+                raise RuntimeError("x must be a CUDA tensor: this package has no CPU path")
+            z, J = self.f(x)
+            ll = J.sum(dim=(1, 2, 3)) + self.prior.log_prob(z).sum(dim=(1, 2, 3))
+            ws = None
+            for name, p in self.named_parameters():             # flow_realnvp.py:362-369
+                if p.requires_grad and name.split(".")[-1] in ("weight_g", "scale"):
+                    ws = p.pow(2).sum() if ws is None else ws + p.pow(2).sum()
+            return ll, ws
         eng = self.engine()
         if torch.is_grad_enabled():
             return _eng.FlowLogProb.apply(_eng.grad_anchor(x.device), x, eng, self.training)
@@ -176,6 +236,11 @@ class RealNVP(nn.Module):
 
     def latent(self, x):
         """(z, per-sample log-det, per-sample log-lik) from the fused path (no full J tensor)."""
+        if not self._native:
+            with torch.no_grad():
+                z, J = self.f(x)
+                ld = J.sum(dim=(1, 2, 3))
+                return z, ld, ld + self.prior.log_prob(z).sum(dim=(1, 2, 3))
         with torch.no_grad():
             ll, ld, z, _w, _ = self.engine().flow_forward(x, self.training, want_z=True, want_ws=False)
         return z, ld, ll

@@ -54,7 +54,7 @@ def _load():
         "rnvp_flow_backward": (i32, [vp, vp, vp, vp, i32, vp, sz, vp]),
         "rnvp_flow_inverse": (i32, [vp, vp, vp, i32, i32, vp, sz, vp]),
         "rnvp_coupling_forward": (i32, [vp, i32, vp, vp, vp, i32, i32, vp, sz, vp]),
-        "rnvp_coupling_inverse": (i32, [vp, i32, vp, vp, i32, i32, vp, sz, vp]),
+        "rnvp_coupling_inverse": (i32, [vp, i32, vp, vp, vp, i32, i32, vp, sz, vp]),
         "rnvp_coupling_backward": (i32, [vp, i32, vp, vp, vp, i32, vp, sz, vp]),
         "rnvp_logit_forward": (i32, [vp, vp, vp, vp, i32, i32, f32, u64, u64, vp]),
         "rnvp_logit_forward_u8": (i32, [vp, vp, vp, vp, i32, i32, f32, u64, u64, vp]),

@@ -281,19 +281,20 @@ class Engine:
             torch._foreach_add_(self._nbt_all, 1)
         return y, logj, ws
 
-    def coupling_inverse(self, idx: int, y: torch.Tensor, training: bool) -> torch.Tensor:
+    def coupling_inverse(self, idx: int, y: torch.Tensor, training: bool):
+        """(x, log_rescale) of ``coupling(y, reverse=True)`` (modules_realnvp.py:284-291, 345-351)."""
         y = _require_cuda(y, "x")
         dev = y.device
         self.ensure_bound(dev)
         B = y.shape[0]
         ws = self.workspace(B, 0, dev)
-        x = torch.empty_like(y)
+        x, logj = torch.empty_like(y), torch.empty_like(y)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        check(lib.rnvp_coupling_inverse(self.handle, idx, ptr(y), ptr(x), B, 1 if training else 0, ptr(ws),
+        check(lib.rnvp_coupling_inverse(self.handle, idx, ptr(y), ptr(x), ptr(logj), B, 1 if training else 0, ptr(ws),
                                         ws.numel(), C.c_void_p(stream)))
         if training:
             torch._foreach_add_(self._nbt_inv, 1)
-        return x
+        return x, logj
 
     def coupling_backward(self, idx: int, dy: torch.Tensor, dlogj: torch.Tensor, ws: torch.Tensor) -> torch.Tensor:
         dev = dy.device

@@ -148,8 +148,9 @@ int rnvp_flow_inverse(rnvp_plan* plan, const float* z_nchw, float* x_nchw, int b
 int rnvp_coupling_forward(rnvp_plan* plan, int coupling, const float* x_nchw, float* y_nchw,
                           float* logJ_nchw, int batch, int training,
                           void* workspace, size_t workspace_bytes, void* stream);
-/* forward(x, reverse=True) */
-int rnvp_coupling_inverse(rnvp_plan* plan, int coupling, const float* y_nchw, float* x_nchw,
+/* forward(x, reverse=True): x and, optionally, the tensor the reference returns beside it -- log_rescale
+ * (modules_realnvp.py:283, 302; zeros on the untouched half of a channelwise coupling), logJ_nchw may be NULL */
+int rnvp_coupling_inverse(rnvp_plan* plan, int coupling, const float* y_nchw, float* x_nchw, float* logJ_nchw,
                           int batch, int training,
                           void* workspace, size_t workspace_bytes, void* stream);
 /* VJP of rnvp_coupling_forward(training=1): dy, dlogJ (B,C,S,S) NCHW upstream

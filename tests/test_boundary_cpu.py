@@ -143,12 +143,22 @@ def test_fused_adam_host_side(pkg):
         pkg.rnvp_optim.Adam(torch.nn.Linear(2, 2))
 
 
-def test_unsupported_hps_raise(pkg):
+def test_non_default_hps_construct_like_the_reference(pkg, golden_dir):
+    """Every hyper-parameter branch builds (module tree, parameter order, requires_grad flags as the reference, see
+    oracle/make_golden_api.py for the value checks on the GPU); on CPU tensors they refuse to run like the rest."""
     prior = torch.distributions.Normal(torch.tensor(0.), torch.tensor(1.))
-    with pytest.raises(NotImplementedError):
-        pkg.RealNVP(3, 32, prior, pkg.Hyperparameters(4, 2, False, True, True, True))
-    with pytest.raises(NotImplementedError):
-        pkg.RealNVP(3, 32, prior, pkg.Hyperparameters(4, 0, True, True, True, True))
+    for bott, skip, wn, cbn, R in [(False, True, True, True, 1), (True, False, True, True, 1), (True, True, False, True, 1),
+                                   (True, True, True, False, 1), (True, True, True, True, 0), (False, False, False, False, 0)]:
+        m = pkg.RealNVP(3, 32, prior, pkg.Hyperparameters(4, R, bott, skip, wn, cbn))
+        names = [n for n, _ in m.named_parameters()]
+        assert any(n.endswith("conv.weight") for n in names) == (not wn)
+        assert any(".core_skips." in n for n in names) == (skip and R > 0)
+        assert any(".res_block.6." in n for n in names) == (bott and R > 0)
+        assert any(n.startswith("s1_ckbd.0.block.1.block.") for n in names) == (R == 0)
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m(torch.zeros(1, 3, 32, 32))
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            m.s1_ckbd[0](torch.zeros(1, 3, 32, 32))
 
 
 def test_order_matrix_matches_index_map(pkg):

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+# gpurun with retries while the pod answers "transient" (nothing charged): tools/gpurun_retry.sh <log> <gpurun args...>
+LOG=$1; shift
+for i in 1 2 3 4 5 6 7 8; do
+  /usr/local/graft/bin/gpurun "$@" > "$LOG" 2>&1
+  if grep -q "status=transient" "$LOG"; then sleep 45; continue; fi
+  break
+done
+tail -15 "$LOG"

@@ -30,6 +30,11 @@ def build() -> bool:
                            dfile=f"reference/{m}.py", doraise=True, optimize=0)
     with open(os.path.join(OUT, "BUILD_INFO"), "w") as f:
         f.write(f"byte-compiled from {REF} by oracle/build_ref.py with python {sys.version.split()[0]}\n")
+    # a checkpoint pair written by the reference's own torch.save calls (interop fixture, oracle/make_golden_api.py)
+    if not os.path.exists(os.path.join(OUT, "ckpt", "expect.pt")):
+        import subprocess
+        subprocess.run([sys.executable, os.path.join(HERE, "make_golden_api.py"), "--checkpoint"], check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return True
 
 

@@ -99,5 +99,57 @@ def main():
     print("written tests/golden/api.pt")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--checkpoint" not in sys.argv:
     main()
+
+
+def checkpoint_case(quiet=False):
+    """A checkpoint pair written by the REFERENCE's own calls (train.py:249-250: torch.save(model.state_dict()),
+    torch.save(optimizer.state_dict())) after two Adam steps of its loop, plus what its third step yields after a
+    resume (train.py:139-154) -- the interop fixture for SURVEY.md 8f-3."""
+    ref_flow, ref_mod, ref_utils = load_reference()
+    # 14 MB of reference-written checkpoint: a build output next to the byte-compiled reference (git-ignored, shipped
+    # to the GPU box with the snapshot), regenerated by __graft_entry__.build() wherever /root/reference is mounted
+    out = os.path.join(HERE, "_ref", "ckpt")
+    os.makedirs(out, exist_ok=True)
+    prior = torch.distributions.Normal(torch.tensor(0.), torch.tensor(1.), validate_args=False)
+
+    def make():
+        torch.manual_seed(999)
+        m = ref_flow.RealNVP(3, 32, prior, ref_utils.Hyperparameters(4, 1, True, True, True, True))
+        return m, torch.optim.Adam(m.parameters(), lr=5e-4, weight_decay=5e-5)
+
+    def batch(i):
+        x_img = O.synthetic_images(6, 3, 32, seed=40 + i)
+        noise = torch.rand(x_img.shape, generator=torch.Generator().manual_seed(90 + i))
+        return O.logit_forward(x_img, noise)            # == utils.logit_transform with this noise (tests pin that)
+
+    def step(m, opt, i):
+        x, logdet = batch(i)
+        opt.zero_grad()
+        logll, ws = m(x)
+        logll = (logll + logdet).mean()
+        (-logll + 5e-5 * ws).backward()
+        opt.step()
+        return float(logll)
+
+    m, opt = make()
+    m.train()
+    l0, l1 = step(m, opt, 0), step(m, opt, 1)
+    torch.save(m.state_dict(), os.path.join(out, "realnvp_state.pt"))
+    torch.save(opt.state_dict(), os.path.join(out, "realnvp_state_optim.pt"))
+    m2, opt2 = make()
+    m2.load_state_dict(torch.load(os.path.join(out, "realnvp_state.pt")))
+    opt2.load_state_dict(torch.load(os.path.join(out, "realnvp_state_optim.pt")))
+    m2.train()
+    l2 = step(m2, opt2, 2)
+    key = "s3_chan.1.block.1.out_block.2.conv.weight_v"
+    torch.save({"logll": [l0, l1, l2], "batches": [batch(i) for i in range(3)],
+                "after_step3": {key: m2.state_dict()[key].clone(), "s1_ckbd.0.scale": m2.state_dict()["s1_ckbd.0.scale"].clone()}},
+               os.path.join(out, "expect.pt"))
+    if not quiet:
+        print("written", out, [os.path.getsize(os.path.join(out, f)) for f in os.listdir(out)])
+
+
+if __name__ == "__main__" and "--checkpoint" in sys.argv:
+    checkpoint_case()

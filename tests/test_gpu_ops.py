@@ -311,7 +311,8 @@ def test_dgrad_bn_relu_fused(pkg, shape):
                                      ptr(gd_d), ptr(dgam), ptr(dbet), 1, 0, _stream()))
     got = dx[..., :cin].permute(0, 3, 1, 2).cpu() - add
     assert rel(got * sure, x.grad * sure) < 5e-3, (rel(got * sure, x.grad * sure), shape)
-    assert rel(dgam, gamma.grad) < 5e-3 and rel(dbet, beta.grad) < 5e-3
+    # per-channel sums of TF32-noisy values with cancellation (K up to 4608 products per element)
+    assert rel(dgam, gamma.grad) < 1e-2 and rel(dbet, beta.grad) < 1e-2
     if ld > cin:
         assert float(dx[..., cin:].abs().max()) == 0.0
     # the rounded variant only differs by the TF32 rounding of its output

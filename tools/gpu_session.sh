@@ -15,6 +15,7 @@ for s in $STEPS; do
     rest_nocpl) RNVP_CPL_EPILOGUE=0 timeout 2400 python -m pytest tests -m gpu -q --timeout 900 --deselect tests/test_gpu_ops.py > $OUT/${TAG}_rest_nocpl.log 2>&1; echo "rest_nocpl rc=$?" ;;
     cpl)   timeout 1200 python -m pytest tests/test_gpu_coupling.py "tests/test_gpu_flow.py::test_golden_model" tests/test_gpu_flow.py::test_cfg_a_against_oracle -m gpu -q --timeout 900 > $OUT/${TAG}_cpl.log 2>&1; echo "cpl rc=$?" ;;
     bench_nocpl) RNVP_CPL_EPILOGUE=0 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $OUT/${TAG}_bench_nocpl.json 2> $OUT/${TAG}_bench_nocpl.err; echo "bench_nocpl rc=$?" ;;
+    dbg)   timeout 600 python tools/debug_conv_bn.py > $OUT/${TAG}_dbg.log 2>&1; echo "dbg rc=$?" ;;
     diag)  timeout 1200 python tools/diag_precision.py > $OUT/${TAG}_diag.log 2>&1; echo "diag rc=$?" ;;
     diagbig) timeout 1500 python tools/diag_precision.py --big > $OUT/${TAG}_diagbig.log 2>&1; echo "diagbig rc=$?" ;;
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?" ;;

@@ -262,9 +262,12 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r 
 
 // BN coefficients of channels [0, kpad) into smem (scale at [c], shift at [kpad_max + c]); channels >= C get 0 / 0.
 // Block `writer` also saves them for the backward pass and updates the running statistics (nn.BatchNorm2d).
-__device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* s_scale, float* s_shift, int kpad, bool writer) {
+// Called by `nthreads` threads numbered `tid` (the transform warps: the loads of the first stages are already in
+// flight while they do this).
+__device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* s_scale, float* s_shift, int kpad, bool writer,
+                                                int tid, int nthreads) {
   const int C = prm.xf_C;
-  for (int c = threadIdx.x; c < kpad; c += blockDim.x) {
+  for (int c = tid; c < kpad; c += nthreads) {
     float sc = 0.f, sh = 0.f;
     if (c < C) {
       if (prm.xf_mode == 2) {
@@ -352,9 +355,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   // chain of successors pile up on the SMs holding shared memory and TMEM columns.
   pdl_wait();
   pdl_trigger();
-  if constexpr (XF) {
-    xf_coefficients(prm, coef, coef + XF_MAX_K, prm.kchunks * 32, blockIdx.x == 0);
-  } else if (coef_in_smem) {
+  if constexpr (!XF) if (coef_in_smem) {
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
       const int k = i / BN, cidx = i % BN;
       coef[i] = cidx < prm.n ? prm.bn_save[(2 + k) * prm.n + cidx] : 0.f;
@@ -436,6 +437,11 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int t = threadIdx.x - 32 * (2 + EW);
     const int j = t & 7, r0 = t >> 3;
     const int Smask = prm.S - 1;
+    // the BN coefficients are only needed here: compute them while the producer's first loads are in flight
+    if constexpr (XF) {
+      xf_coefficients(prm, coef, coef + XF_MAX_K, prm.kchunks * 32, blockIdx.x == 0, t, 32 * TcCfg<BN, XF>::XF_WARPS);
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * TcCfg<BN, XF>::XF_WARPS) : "memory");
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x) {

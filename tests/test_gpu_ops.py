@@ -183,7 +183,9 @@ def _wn_operands(pkg, v, gg):
     kpad, npad, kpad_b, npad_b = _pad(cin, 32), _pad(cout, 16), _pad(cout, 32), _pad(cin, 16)
     arena = torch.empty(k * k * npad * kpad + k * k * npad_b * kpad_b, device=DEV)
     wf, wb = arena[: k * k * npad * kpad], arena[k * k * npad * kpad:]
-    check(lib.rnvp_weightnorm_forward(ptr(v.to(DEV)), ptr(gg.to(DEV)), ptr(wf), ptr(wb), cout, cin, k, _stream()))
+    vd, gd = v.to(DEV), gg.to(DEV)       # named: a temporary's block could be handed to the next allocation (and be
+    check(lib.rnvp_weightnorm_forward(ptr(vd), ptr(gd), ptr(wf), ptr(wb), cout, cin, k, _stream()))   # overwritten by
+    torch.cuda.current_stream().synchronize()                                     # its H2D copy) before the kernel ran
     return wf, wb
 
 

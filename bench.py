@@ -40,6 +40,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config 2: 256)")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling: the WHOLE job's batch, split evenly over the GPUs (BASELINE configs[3]: 4096 "
+                         "samples, configs[4]: global batch 2048); overrides --batch")
     ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
     ap.add_argument("--mode", default="train", choices=["train", "sample"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -389,6 +392,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cabi.check(cabi.lib.rnvp_device_ok())
+    if args.global_batch:
+        if args.global_batch % world:
+            raise SystemExit(f"--global-batch {args.global_batch} is not divisible by {world} GPUs")
+        args.batch = args.global_batch // world
     B = args.batch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
@@ -398,10 +405,10 @@ def run_b200(args):
                         pkg.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True),
                         **({} if CFG["num_scales"] == 5 else {"num_scales": CFG["num_scales"]})).to(dev)
     model.set_math(args.math)
-    if world > 1:
+    if world > 1 and args.mode == "train":              # sampling shards by batch with no communication
         import rnvp_dp
         model = rnvp_dp.DataParallel(model)
-    net = model.module if world > 1 else model
+    net = model.module if (world > 1 and args.mode == "train") else model
     if args.optimizer == "fused":
         opt = pkg.rnvp_optim.Adam(model, lr=5e-4, weight_decay=5e-5)           # train.py:134 hyper-parameters
     else:
@@ -431,6 +438,7 @@ def run_b200(args):
 
     net.train(args.mode == "train")
     if args.mode == "sample":
+        torch.manual_seed(4321 + rank)                      # every rank draws its own z
         # converged running statistics first (a sampler is used after training); the training workspace of the
         # full sampling batch would not fit, so these steps use at most 256 images
         net.train()
@@ -625,7 +633,8 @@ def run_b200(args):
         tr_flops = 3 * GFLOP_FWD_PER_IMG if args.mode == "train" else GFLOP_FWD_PER_IMG
         out = {"metric": METRIC if args.mode == "train" else "sample imgs/s RealNVP 64x64x3",
                "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-               "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms / args.steps, "higher_is_better": True,
+               "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
                "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
                "config": {"workload": ("RealNVP 32x32x3 -> 16x16x6, 8 res-blocks / 64 features (BASELINE configs[2])"
                                        if args.config == "c3" else
@@ -635,7 +644,7 @@ def run_b200(args):
                           "batch_per_gpu": B, "global_batch": B * world, "mode": args.mode,
                           "parallelism": f"dp{world}" if world > 1 else "single",
                           **({"bn_stat_exchange": model.stat_exchange, "grad_allreduce": "nccl, bucketed, overlapped"}
-                             if world > 1 else {}),
+                             if (world > 1 and args.mode == "train") else {}),
                           "l2": "inputs larger than L2: the per-step working set (tens of GB of activations) exceeds the 126 MB L2",
                           "optimizer": ("rnvp_optim.Adam (one fused launch, clears the gradients)"
                                         if args.optimizer == "fused" else "torch.optim.Adam(fused=True)") +

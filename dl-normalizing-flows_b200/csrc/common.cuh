@@ -142,6 +142,72 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 __device__ __forceinline__ float maybe_round(float x, int on) { return on ? round_tf32(x) : x; }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-shot all-reduce of a small double vector over NVLink peer memory, folded INTO the kernel that consumes the
+// vector (the batch-norm statistic exchange of data-parallel training, dp.cu).  Every rank owns an inbox
+// [world][2 slots][cap] doubles + [world] sequence flags that its peers map through CUDA IPC.  One CTA of the consumer
+// (`pusher`) stores the local vector into slot (seq & 1) of every rank's inbox -- remote stores through the NVSwitch --
+// and publishes `seq` with system-scope release stores; EVERY CTA then waits until all ranks' numbers have arrived in
+// the own inbox, after which dp_reduced() returns the rank-ordered (hence bit-identical on all ranks) sum of an
+// element.  A rank is at most one exchange ahead of the slowest one: finishing exchange k+1 needs every peer's flag
+// k+1, which a peer publishes only from the kernel that FOLLOWS the one that read exchange k.  Compared with the
+// stand-alone exchange kernel this removes one launch + its stream dependency from the critical path per reduction.
+// Failures (a peer that never arrives, diverged call sequences) set the sticky error word: every later entry point of
+// the plan then fails with RNVP_ERR_STATE (the numbers of the step in flight are garbage, and known to be).
+// ---------------------------------------------------------------------------------------------------------
+struct DpXchg {
+  void* const* peers = nullptr;      // device array: inbox base of every rank; null = no exchange (single process,
+  int rank = 0, world = 1, cap = 0;  //   or the vector was already reduced by the stand-alone kernel / NCCL)
+  unsigned long long seq = 0;
+  int* err = nullptr;                // sticky error word (mapped host memory)
+  __host__ __device__ bool on() const { return peers != nullptr; }
+};
+// bar_id / nthreads: the named barrier and thread count of the calling group (all of its threads must call);
+// tid = index of the caller within the group
+__device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __restrict__ local, int n, bool pusher,
+                                            int tid, int nthreads, int bar_id) {
+  if (!x.on()) return;
+  const int slot = (int)(x.seq & 1ull);
+  const size_t flag_off = (size_t)x.world * 2 * x.cap * sizeof(double);
+  if (pusher) {
+    for (int p = 0; p < x.world; ++p) {
+      double* dst = reinterpret_cast<double*>(x.peers[p]) + ((size_t)x.rank * 2 + slot) * x.cap;
+      for (int i = tid; i < n; i += nthreads) dst[i] = local[i];
+    }
+    __threadfence_system();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    if (tid < x.world) {
+      unsigned long long* pflag =
+          reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x.peers[tid]) + flag_off) + x.rank;
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pflag), "l"(x.seq) : "memory");
+    }
+  }
+  if (tid < x.world) {
+    const unsigned long long* mine =
+        reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(x.peers[x.rank]) + flag_off) + tid;
+    const long long t0 = clock64();
+    unsigned long long v = 0;
+    for (unsigned it = 1;; ++it) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= x.seq) break;
+      if ((it & 0xffffu) == 0) {                                           // rarely: the error word lives in host memory
+        if (*reinterpret_cast<volatile int*>(x.err) != 0) break;           // an earlier exchange already failed
+        if (clock64() - t0 > 240000000000ll) break;                        // ~2 min: the peer is gone
+      }
+    }
+    if (v < x.seq) *reinterpret_cast<volatile int*>(x.err) = 1;
+    else if (v > x.seq + 1) *reinterpret_cast<volatile int*>(x.err) = 2;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ double dp_reduced(const DpXchg& x, const double* __restrict__ local, int i) {
+  if (!x.on()) return local[i];
+  const double* inbox = reinterpret_cast<const double*>(x.peers[x.rank]) + (size_t)(x.seq & 1ull) * x.cap;
+  double s = 0.0;
+  for (int p = 0; p < x.world; ++p) s += __ldcg(inbox + (size_t)p * 2 * x.cap + i);   // L2: written by the peers
+  return s;
+}
+
 // mean / rstd / scale / shift of one BN channel from (sum, sumsq) over `count` values
 struct BnCoef { float mean, rstd, scale, shift, var; };
 __device__ __forceinline__ BnCoef bn_coef_from_sums(double s, double ss, double count, float gamma, float beta) {

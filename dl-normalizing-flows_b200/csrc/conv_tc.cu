@@ -253,6 +253,7 @@ struct ConvTcParams {
   float* xf_rm;
   float* xf_rv;
   float* xf_save;                    // [4C] mean, rstd, scale, shift
+  DpXchg xf_xg;                      // data parallel: reduce xf_sums over the ranks in the prologue (mode 1)
   // coupling epilogue (CPL kernels: the s/t net's out conv, n_tiles == 1)
   CplEpilogue cpl;
 };
@@ -267,6 +268,7 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r 
 __device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* s_scale, float* s_shift, int kpad, bool writer,
                                                 int tid, int nthreads) {
   const int C = prm.xf_C;
+  if (prm.xf_mode == 1) dp_exchange(prm.xf_xg, prm.xf_sums, 2 * C, writer, tid, nthreads, 2);
   for (int c = tid; c < kpad; c += nthreads) {
     float sc = 0.f, sh = 0.f;
     if (c < C) {
@@ -275,7 +277,8 @@ __device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* 
         sh = prm.xf_save[3 * C + c];
       } else {
         const BnCoef k = prm.xf_mode == 1
-                             ? bn_coef_from_sums(prm.xf_sums[c], prm.xf_sums[C + c], prm.xf_count, prm.xf_gamma[c], prm.xf_beta[c])
+                             ? bn_coef_from_sums(dp_reduced(prm.xf_xg, prm.xf_sums, c), dp_reduced(prm.xf_xg, prm.xf_sums, C + c),
+                                                 prm.xf_count, prm.xf_gamma[c], prm.xf_beta[c])
                              : bn_coef_from_running(prm.xf_rm[c], prm.xf_rv[c], prm.xf_gamma[c], prm.xf_beta[c]);
         sc = k.scale;
         sh = k.shift;
@@ -977,6 +980,7 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
     RNVP_REQUIRE(x.mode != 1 || (x.sums && x.save), "BN prologue: training mode needs sums and save");
     prm.xf_mode = x.mode; prm.xf_C = x.C; prm.xf_sums = x.sums; prm.xf_count = x.count;
     prm.xf_gamma = x.gamma; prm.xf_beta = x.beta; prm.xf_rm = x.run_mean; prm.xf_rv = x.run_var; prm.xf_save = x.save;
+    prm.xf_xg = x.xg;
     if (a.cpl && a.cpl->mode) {
       RNVP_REQUIRE(a.n <= 128 && a.bias && !a.res && a.n == 2 * a.cpl->g.cio,
                    "coupling epilogue: the out conv must have a bias, no residual and 2*cio <= 128 outputs");

@@ -8,6 +8,7 @@
 //        a synchronised BN, issued in-stream between the producer and consumer kernels.
 // NCCL is resolved with dlopen at first use so that the library loads on a box without it.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <mutex>
 #include "kernels.h"
 
@@ -175,6 +176,24 @@ int dp_check_equal_batches(DpState* dp, int batch, double* scratch2, cudaStream_
 }
 int dp_sticky_error(const DpState* dp) {
   return dp->xchg_err_host ? *reinterpret_cast<volatile int*>(dp->xchg_err_host) : 0;
+}
+
+int dp_fused_exchange(DpState* dp, double* buf, size_t n, cudaStream_t st, DpXchg* out) {
+  *out = DpXchg();
+  if (dp->world <= 1) return RNVP_OK;
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("RNVP_DP_FUSED");
+    fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (fused && dp->xchg_ready && (int)n <= dp->xchg_cap) {
+    out->peers = dp->xchg_peers_dev;
+    out->rank = dp->rank; out->world = dp->world; out->cap = dp->xchg_cap;
+    out->seq = ++dp->xchg_seq;
+    out->err = dp->xchg_err;
+    return RNVP_OK;
+  }
+  return dp_allreduce_doubles(dp, buf, n, st);
 }
 
 static int launch_bucket(DpState* dp, int64_t begin, int64_t end, cudaStream_t main) {

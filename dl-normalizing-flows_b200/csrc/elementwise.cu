@@ -252,19 +252,20 @@ int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream
 __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict__ h, int64_t n4, int C, int ld,
                                const double* __restrict__ sums, double count,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                               float* run_mean, float* run_var, float* save, int mode, int rnd, int rev) {
+                               float* run_mean, float* run_var, float* save, int mode, int rnd, int rev, DpXchg xg) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
   float* s_shift = sm + C;
+  if (mode == 1) dp_exchange(xg, sums, 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (mode == 2) {
       s_scale[c] = save[2 * C + c];
       s_shift[c] = save[3 * C + c];
       continue;
     }
-    BnCoef k = mode == 1 ? bn_coef_from_sums(sums[c], sums[C + c], count, gamma[c], beta[c])
+    BnCoef k = mode == 1 ? bn_coef_from_sums(dp_reduced(xg, sums, c), dp_reduced(xg, sums, C + c), count, gamma[c], beta[c])
                          : bn_coef_from_running(run_mean[c], run_var[c], gamma[c], beta[c]);
     s_scale[c] = k.scale;
     s_shift[c] = k.shift;
@@ -308,13 +309,13 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
 }
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var, float* save, int mode,
-              int tf32_round, cudaStream_t st) {
+              int tf32_round, cudaStream_t st, DpXchg xg) {
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(C % 4 == 0 && ld % 4 == 0 && ld >= C, "bn_relu: C=%d ld=%d unsupported", C, ld);
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_relu_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        2 * C * sizeof(float), st, (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta,
-                       run_mean, run_var, save, mode, tf32_round, next_sweep_dir()));
+                       run_mean, run_var, save, mode, tf32_round, next_sweep_dir(), xg));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -407,16 +408,18 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
                                     float4* dx, const float4* add, int64_t n4, int C, int ld,
                                     const float* __restrict__ save, const double* __restrict__ sums2,
                                     double count, const float* __restrict__ gamma, float* dgamma,
-                                    float* dbeta, float inv_world, int raw_x_sums, int rnd, int rev) {
+                                    float* dbeta, float inv_world, int raw_x_sums, int rnd, int rev, DpXchg xg) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
+  dp_exchange(xg, sums2, 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float rstd = save[C + c];
     // second statistic: sum g*xhat, or (fused dgrad epilogue) sum g*x which maps to it linearly
-    double s1 = sums2[c];
-    double s2 = raw_x_sums ? (double)rstd * (sums2[C + c] - (double)save[c] * s1) : sums2[C + c];
+    double s1 = dp_reduced(xg, sums2, c);
+    const double s2raw = dp_reduced(xg, sums2, C + c);
+    double s2 = raw_x_sums ? (double)rstd * (s2raw - (double)save[c] * s1) : s2raw;
     s_a[c] = gamma[c] * rstd;
     s_m1[c] = (float)(s1 / count);
     s_m2[c] = (float)(s2 / count);
@@ -467,12 +470,13 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
 }
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st) {
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st,
+                   DpXchg xg) {
   if (P == 0) return RNVP_OK;
   int64_t n4 = (int64_t)P * ld / 4;
   RNVP_CUDA(launch_pdl(bn_bwd_apply_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        5 * C * sizeof(float), st, (const float4*)gm, (const float4*)x, (float4*)dx, (const float4*)add, n4, C, ld,
-                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, tf32_round, next_sweep_dir()));
+                       save, sums2, count, gamma, dgamma, dbeta, inv_world, raw_x_sums, tf32_round, next_sweep_dir(), xg));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

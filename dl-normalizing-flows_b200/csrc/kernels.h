@@ -34,9 +34,10 @@ int k_logit_inv(const float* y, float* x, size_t n, float constraint, cudaStream
 //           save[4C] = mean,rstd,scale,shift; running stats updated by block 0
 //   mode 0 (eval): running statistics
 //   mode 2 (recompute in backward): scale/shift read back from `save`
+// xg: data parallel -- the cross-rank reduction of `sums` happens inside this kernel (common.cuh, DpXchg)
 int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums, double count,
               const float* gamma, const float* beta, float* run_mean, float* run_var,
-              float* save, int mode, int tf32_round, cudaStream_t st);
+              float* save, int mode, int tf32_round, cudaStream_t st, DpXchg xg = DpXchg());
 // gm = g * 1[h>0] written to gm_out; sums2[0:C] += sum gm, sums2[C:2C] += sum gm*xhat
 int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C, int ld,
                     const float* save, double* sums2, cudaStream_t st);
@@ -45,7 +46,8 @@ int k_bn_bwd_reduce(const float* g, const float* x, float* gm_out, int P, int C,
 // tf32_round: dx is the dy operand of a dgrad / wgrad MMA -> round to nearest TF32
 int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add, int P, int C, int ld,
                    const float* save, const double* sums2, double count, const float* gamma,
-                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st);
+                   float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st,
+                   DpXchg xg = DpXchg());
 
 // ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
@@ -132,6 +134,10 @@ struct DpState {
   bool xchg_ready = false;
 };
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st);
+// descriptor for a reduction of n doubles folded into the consumer kernel (takes the next sequence number), or a
+// disabled descriptor after having reduced `buf` in place the stand-alone way (exchange closed, n too large,
+// RNVP_DP_FUSED=0)
+int dp_fused_exchange(DpState* dp, double* buf, size_t n, cudaStream_t st, DpXchg* out);
 // reduce (B, B^2) over the ranks and flag unequal local batches in the sticky error word (scratch2: 2 device doubles)
 int dp_check_equal_batches(DpState* dp, int batch, double* scratch2, cudaStream_t st);
 int dp_sticky_error(const DpState* dp);   // current value of the sticky error word (host read, no synchronisation)
@@ -152,6 +158,7 @@ struct BnPrologue {
   float* run_mean;     // updated in mode 1
   float* run_var;
   float* save;         // [4C] mean, rstd, scale, shift: written in mode 1, read in mode 2
+  DpXchg xg;           // data parallel, mode 1: reduce `sums` over the ranks inside the kernel's prologue
 };
 // The affine coupling fused into the epilogue of the s/t network's out conv (modules_realnvp.py:277-301, 339-361):
 // the accumulator row of a pixel holds (t | l); the epilogue forms s = (scale*tanh(l)+shift)*(1-m), t*(1-m) and

@@ -465,6 +465,12 @@ int sync_stats(const Ctx& c, double* buf, size_t n) {
   if (c.p->world > 1) return dp_allreduce_doubles(&c.p->dp, buf, n, c.st);
   return RNVP_OK;
 }
+// the same reduction folded into the kernel that consumes `buf` (bn_relu, bn_bwd_apply, the BN-prologue conv)
+int sync_stats_fused(const Ctx& c, double* buf, size_t n, DpXchg* xg) {
+  *xg = DpXchg();
+  if (c.p->world > 1) return dp_fused_exchange(&c.p->dp, buf, n, c.st, xg);
+  return RNVP_OK;
+}
 
 ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
                    const float* bias, const float* res, double* stats) {
@@ -511,6 +517,7 @@ int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, 
   x.gamma = P_<float>(p, d, ci, b.slot_w); x.beta = P_<float>(p, d, ci, b.slot_b);
   x.run_mean = P_<float>(p, d, ci, b.slot_rm); x.run_var = P_<float>(p, d, ci, b.slot_rv);
   x.save = c.save(b.save);
+  if (training) RNVP_TRY(sync_stats_fused(c, c.sf(b.sf), 2 * b.C, &x.xg));
   a.xf = &x;
   a.cpl = cpl;
   return k_conv_fwd_tf32(a, c.st);
@@ -562,12 +569,13 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
   float* Hs = c.scratch();
   auto bn = [&](int bi, const float* x) -> int {
     const BnDesc& b = d.bns[bi];
-    if (training) RNVP_TRY(sync_stats(c, c.sf(b.sf), 2 * b.C));
+    DpXchg xg;
+    if (training) RNVP_TRY(sync_stats_fused(c, c.sf(b.sf), 2 * b.C, &xg));
     ProfScope ps(PROF_BN, S, 0, b.C, b.C, c.st);
     H = A.keep_h ? c.act(ci, A.h[bi]) : Hs;
     return k_bn_relu(x, H, Pn, b.C, ld, training ? c.sf(b.sf) : nullptr, count, P_<float>(p, d, ci, b.slot_w),
                      P_<float>(p, d, ci, b.slot_b), P_<float>(p, d, ci, b.slot_rm),
-                     P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, rnd, c.st);
+                     P_<float>(p, d, ci, b.slot_rv), c.save(b.save), training ? 1 : 0, rnd, c.st, xg);
   };
   auto st_of = [&](int bi) { return training ? c.sf(d.bns[bi].sf) : nullptr; };
   const ConvDesc* cv = d.convs.data();
@@ -575,10 +583,8 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
   // y = conv(relu(bn_bi(x))): one kernel with the BN prologue, or bn_relu + conv
   auto bn_conv = [&](int bi, const float* x, const ConvDesc& cvx, float* y, int ldy, const float* b, const float* res,
                      double* stats, bool operand_out) -> int {
-    if (bn_fused(p, d, bi)) {
-      if (training) RNVP_TRY(sync_stats(c, c.sf(d.bns[bi].sf), 2 * d.bns[bi].C));
+    if (bn_fused(p, d, bi))
       return run_conv_bn(c, ci, cvx, bi, training, count, x, S, y, ldy, b, res, stats, operand_out);
-    }
     RNVP_TRY(bn(bi, x));
     return run_conv(c, cvx, false, H, S, y, ldy, b, res, stats, operand_out);
   };
@@ -607,7 +613,6 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
   const ConvDesc& oc = cv[2 + 4 * R];
   if (cpl) {
     RNVP_REQUIRE(xf, "internal: coupling epilogue without the BN-prologue kernel");
-    if (training) RNVP_TRY(sync_stats(c, c.sf(d.bns[3 * R].sf), 2 * d.bns[3 * R].C));
     return run_conv_bn(c, ci, oc, 3 * R, training, count, c.act(ci, A.skip), S, c.act(ci, A.st), d.cst_pad, bias(oc),
                        nullptr, nullptr, false, cpl);
   }
@@ -668,10 +673,11 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     }
     ProfScope ps(PROF_BN_BWD, S, 0, b.C, b.C, c.st);
     if (!fused) RNVP_TRY(k_bn_bwd_reduce(g, x, g, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), c.st));
-    RNVP_TRY(sync_stats(c, c.sb(b.sb), 2 * b.C));
+    DpXchg xg;
+    RNVP_TRY(sync_stats_fused(c, c.sb(b.sb), 2 * b.C, &xg));
     return k_bn_bwd_apply(g, x, out, add, Pn, b.C, ld, c.save(b.save), c.sb(b.sb), count,
                           P_<float>(p, d, ci, b.slot_w), G_(p, ci, b.slot_w), G_(p, ci, b.slot_b),
-                          1.0f / p->world, fused ? 1 : 0, operand_out && p->math == RNVP_MATH_TF32, c.st);
+                          1.0f / p->world, fused ? 1 : 0, operand_out && p->math == RNVP_MATH_TF32, c.st, xg);
   };
   const ConvDesc* cv = d.convs.data();
   const ConvDesc& oc = cv[2 + 4 * R];

@@ -671,10 +671,11 @@ def main():
         _main(args)
     finally:
         sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        os.close(real_stdout)
+        # the record goes straight to the real stdout; fd 1 STAYS pointed at stderr, so whatever a library still
+        # prints at teardown (NCCL_DEBUG=INFO's communicator-destroy lines) cannot follow the JSON line
         if _RECORD:
-            print(_RECORD[-1], flush=True)
+            os.write(real_stdout, (_RECORD[-1] + "\n").encode())
+        os.close(real_stdout)
 
 
 _RECORD = []

@@ -169,6 +169,11 @@ __device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __res
   if (!x.on()) return;
   const int slot = (int)(x.seq & 1ull);
   const size_t flag_off = (size_t)x.world * 2 * x.cap * sizeof(double);
+  // [world] peer flags, then one LOCAL "exchange seq has arrived" word: only the pusher CTA polls the peers'
+  // system-scope flags (hundreds of CTAs hammering them delays the very stores they wait for -- measured); the other
+  // CTAs of the grid wait for the pusher's gpu-scope word
+  unsigned long long* my_flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x.peers[x.rank]) + flag_off);
+  unsigned long long* arrived = my_flags + x.world;
   if (pusher) {
     for (int p = 0; p < x.world; ++p) {
       double* dst = reinterpret_cast<double*>(x.peers[p]) + ((size_t)x.rank * 2 + slot) * x.cap;
@@ -180,25 +185,33 @@ __device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __res
       unsigned long long* pflag =
           reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(x.peers[tid]) + flag_off) + x.rank;
       asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pflag), "l"(x.seq) : "memory");
+      const long long t0 = clock64();
+      unsigned long long v = 0;
+      for (unsigned it = 1;; ++it) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + tid) : "memory");
+        if (v >= x.seq) break;
+        if ((it & 0xffffu) == 0) {                                         // rarely: the error word lives in host memory
+          if (*reinterpret_cast<volatile int*>(x.err) != 0) break;         // an earlier exchange already failed
+          if (clock64() - t0 > 240000000000ll) break;                      // ~2 min: the peer is gone
+        }
+      }
+      if (v < x.seq) *reinterpret_cast<volatile int*>(x.err) = 1;
+      else if (v > x.seq + 1) *reinterpret_cast<volatile int*>(x.err) = 2;
     }
-  }
-  if (tid < x.world) {
-    const unsigned long long* mine =
-        reinterpret_cast<const unsigned long long*>(reinterpret_cast<const char*>(x.peers[x.rank]) + flag_off) + tid;
-    const long long t0 = clock64();
-    unsigned long long v = 0;
-    for (unsigned it = 1;; ++it) {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-      if (v >= x.seq) break;
-      if ((it & 0xffffu) == 0) {                                           // rarely: the error word lives in host memory
-        if (*reinterpret_cast<volatile int*>(x.err) != 0) break;           // an earlier exchange already failed
-        if (clock64() - t0 > 240000000000ll) break;                        // ~2 min: the peer is gone
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(arrived), "l"(x.seq) : "memory");
+  } else {
+    if (tid == 0) {
+      unsigned long long v = 0;
+      for (unsigned it = 1;; ++it) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(arrived) : "memory");
+        if (v >= x.seq) break;
+        __nanosleep(100);
+        if ((it & 0xfffffu) == 0 && *reinterpret_cast<volatile int*>(x.err) != 0) break;
       }
     }
-    if (v < x.seq) *reinterpret_cast<volatile int*>(x.err) = 1;
-    else if (v > x.seq + 1) *reinterpret_cast<volatile int*>(x.err) = 2;
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
-  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ double dp_reduced(const DpXchg& x, const double* __restrict__ local, int i) {
   if (!x.on()) return local[i];

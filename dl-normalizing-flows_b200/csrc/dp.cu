@@ -264,7 +264,8 @@ int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64) {
   RNVP_REQUIRE(dp->world > 1 && dp->world <= 16, "statistic exchange: world size %d unsupported (2..16)", dp->world);
   RNVP_REQUIRE(dp->xchg_local == nullptr, "statistic exchange already allocated");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
-  const size_t bytes = (size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)dp->world * sizeof(unsigned long long);
+  // [world][2][cap] doubles, [world] peer sequence flags, 1 local "arrived" word (fused exchange, common.cuh)
+  const size_t bytes = (size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)(dp->world + 1) * sizeof(unsigned long long);
   RNVP_CUDA(cudaMalloc(&dp->xchg_local, bytes));
   RNVP_CUDA(cudaMemset(dp->xchg_local, 0, bytes));
   RNVP_CUDA(cudaHostAlloc(&dp->xchg_err_host, sizeof(int), cudaHostAllocMapped));

@@ -148,8 +148,8 @@ __device__ __forceinline__ float maybe_round(float x, int on) { return on ? roun
 // [world][2 slots][cap] doubles + [world] sequence flags that its peers map through CUDA IPC.  One CTA of the consumer
 // (`pusher`) stores the local vector into slot (seq & 1) of every rank's inbox -- remote stores through the NVSwitch --
 // and publishes `seq` with system-scope release stores; EVERY CTA then waits until all ranks' numbers have arrived in
-// the own inbox, after which dp_reduced() returns the rank-ordered (hence bit-identical on all ranks) sum of an
-// element.  A rank is at most one exchange ahead of the slowest one: finishing exchange k+1 needs every peer's flag
+// the own inbox, and the pusher replaces the local vector by the rank-ordered (hence bit-identical on all ranks) sum,
+// which dp_reduced() reads.  A rank is at most one exchange ahead of the slowest one: finishing exchange k+1 needs every peer's flag
 // k+1, which a peer publishes only from the kernel that FOLLOWS the one that read exchange k.  Compared with the
 // stand-alone exchange kernel this removes one launch + its stream dependency from the critical path per reduction.
 // Failures (a peer that never arrives, diverged call sequences) set the sticky error word: every later entry point of
@@ -164,7 +164,7 @@ struct DpXchg {
 };
 // bar_id / nthreads: the named barrier and thread count of the calling group (all of its threads must call);
 // tid = index of the caller within the group
-__device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __restrict__ local, int n, bool pusher,
+__device__ __forceinline__ void dp_exchange(const DpXchg& x, double* local, int n, bool pusher,
                                             int tid, int nthreads, int bar_id) {
   if (!x.on()) return;
   const int slot = (int)(x.seq & 1ull);
@@ -199,6 +199,15 @@ __device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __res
       else if (v > x.seq + 1) *reinterpret_cast<volatile int*>(x.err) = 2;
     }
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    // rank-ordered sum, written back over the local vector: the rest of the grid reads plain reduced sums
+    const double* inbox = reinterpret_cast<const double*>(x.peers[x.rank]) + (size_t)slot * x.cap;
+    for (int i = tid; i < n; i += nthreads) {
+      double s = 0.0;
+      for (int p = 0; p < x.world; ++p) s += __ldcg(inbox + (size_t)p * 2 * x.cap + i);
+      local[i] = s;
+    }
+    __threadfence();
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
     if (tid == 0) asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(arrived), "l"(x.seq) : "memory");
   } else {
     if (tid == 0) {
@@ -213,12 +222,9 @@ __device__ __forceinline__ void dp_exchange(const DpXchg& x, const double* __res
     asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
   }
 }
-__device__ __forceinline__ double dp_reduced(const DpXchg& x, const double* __restrict__ local, int i) {
-  if (!x.on()) return local[i];
-  const double* inbox = reinterpret_cast<const double*>(x.peers[x.rank]) + (size_t)(x.seq & 1ull) * x.cap;
-  double s = 0.0;
-  for (int p = 0; p < x.world; ++p) s += __ldcg(inbox + (size_t)p * 2 * x.cap + i);   // L2: written by the peers
-  return s;
+// element i of the (reduced) vector; after dp_exchange the pusher CTA has overwritten `local` with the global sums
+__device__ __forceinline__ double dp_reduced(const DpXchg& x, const double* local, int i) {
+  return x.on() ? __ldcg(local + i) : local[i];      // L2: written by another CTA of this grid
 }
 
 // mean / rstd / scale / shift of one BN channel from (sum, sumsq) over `count` values

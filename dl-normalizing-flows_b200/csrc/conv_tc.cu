@@ -237,6 +237,8 @@ struct ConvTcParams {
   const float* bn_save;              // non-null: fused ReLU+BN backward epilogue (tmR maps the raw activations)
   int has_res;
   int round_out;                     // round the result to TF32 (cvt.rna): it is the raw operand of another conv MMA
+  const float* post_scale;           // eval mode: y = relu(y * post_scale[n] + post_shift[n]) -- the NEXT layer's batch
+  const float* post_shift;           //   norm (fixed affine on running statistics) + ReLU applied where y is produced
   int P, n, taps, kchunks;           // kchunks = kpad / 32
   int S, log2S;
   int m_tiles, n_tiles;
@@ -268,7 +270,7 @@ __device__ __forceinline__ uint32_t swz_off(int r, int j) { return (uint32_t)(r 
 __device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* s_scale, float* s_shift, int kpad, bool writer,
                                                 int tid, int nthreads) {
   const int C = prm.xf_C;
-  if (prm.xf_mode == 1) dp_exchange(prm.xf_xg, prm.xf_sums, 2 * C, writer, tid, nthreads, 2);
+  if (prm.xf_mode == 1) dp_exchange(prm.xf_xg, const_cast<double*>(prm.xf_sums), 2 * C, writer, tid, nthreads, 2);
   for (int c = tid; c < kpad; c += nthreads) {
     float sc = 0.f, sh = 0.f;
     if (c < C) {
@@ -680,6 +682,20 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
           }
         }
+        if (prm.post_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 sc4 = make_float4(0.f, 0.f, 0.f, 0.f), sh4 = sc4;
+            if (nb + j + 4 <= prm.n) {                      // n % 4 == 0 (checked by the launcher)
+              sc4 = __ldg(reinterpret_cast<const float4*>(prm.post_scale + nb + j));
+              sh4 = __ldg(reinterpret_cast<const float4*>(prm.post_shift + nb + j));
+            }
+            v[j] = fmaxf(fmaf(v[j], sc4.x, sh4.x), 0.f);
+            v[j + 1] = fmaxf(fmaf(v[j + 1], sc4.y, sh4.y), 0.f);
+            v[j + 2] = fmaxf(fmaf(v[j + 2], sc4.z, sh4.z), 0.f);
+            v[j + 3] = fmaxf(fmaf(v[j + 3], sc4.w, sh4.w), 0.f);
+          }
+        }
         if (prm.round_out) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
@@ -954,7 +970,8 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int bw, bh, bn;
   if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0) {
-    RNVP_REQUIRE(a.bn_x == nullptr && a.xf == nullptr, "fused BN prologue / backward epilogue need the tensor-core kernel");
+    RNVP_REQUIRE(a.bn_x == nullptr && a.xf == nullptr && a.post_scale == nullptr,
+                 "fused BN prologue / epilogues need the tensor-core kernel");
     return k_conv_fwd_fp32(a, st);          // shapes the TMA box cannot express: CUDA-core kernel
   }
   RNVP_REQUIRE(a.bn_x == nullptr || (a.res == nullptr && a.bias == nullptr && a.n % 4 == 0 && a.bn_save && a.stats),
@@ -966,6 +983,9 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   prm.bias = a.bias; prm.has_res = a.res != nullptr || a.bn_x != nullptr; prm.stats = a.stats;
   prm.bn_save = a.bn_x ? a.bn_save : nullptr;
   prm.round_out = a.round_out;
+  RNVP_REQUIRE((a.post_scale == nullptr) == (a.post_shift == nullptr) && (a.post_scale == nullptr || (a.n % 4 == 0 && a.bn_x == nullptr)),
+               "conv: the post-affine epilogue needs scale and shift, n % 4 == 0 and no fused BN backward");
+  prm.post_scale = a.post_scale; prm.post_shift = a.post_shift;
   prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
   prm.S = a.S;
   prm.log2S = 0;

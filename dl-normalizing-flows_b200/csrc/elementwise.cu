@@ -258,7 +258,7 @@ __global__ void bn_relu_kernel(const float4* __restrict__ x, float4* __restrict_
   extern __shared__ float sm[];          // scale[C], shift[C]
   float* s_scale = sm;
   float* s_shift = sm + C;
-  if (mode == 1) dp_exchange(xg, sums, 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
+  if (mode == 1) dp_exchange(xg, const_cast<double*>(sums), 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     if (mode == 2) {
       s_scale[c] = save[2 * C + c];
@@ -316,6 +316,22 @@ int k_bn_relu(const float* x, float* h, int P, int C, int ld, const double* sums
   RNVP_CUDA(launch_pdl(bn_relu_kernel, dim3(grid_for(n4, kThreads * 4, kNumSMs * 8)), dim3(kThreads),
                        2 * C * sizeof(float), st, (const float4*)x, (float4*)h, n4, C, ld, sums, count, gamma, beta,
                        run_mean, run_var, save, mode, tf32_round, next_sweep_dir(), xg));
+  RNVP_LAUNCH_CHECK();
+  return RNVP_OK;
+}
+
+__global__ void bn_eval_coef_kernel(const BnEvalJob* __restrict__ jobs, float* __restrict__ save_base) {
+  const BnEvalJob j = jobs[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= j.C) return;
+  const BnCoef k = bn_coef_from_running(j.rm[c], j.rv[c], j.gamma[c], j.beta[c]);
+  float* save = save_base + j.save_off;
+  save[2 * j.C + c] = k.scale;
+  save[3 * j.C + c] = k.shift;
+}
+int k_bn_eval_coefs(const BnEvalJob* jobs_dev, int njobs, int max_c, float* save_base, cudaStream_t st) {
+  if (njobs == 0) return RNVP_OK;
+  bn_eval_coef_kernel<<<dim3(ceil_div(max_c, 128), njobs), 128, 0, st>>>(jobs_dev, save_base);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -413,7 +429,7 @@ __global__ void bn_bwd_apply_kernel(const float4* gm, const float4* __restrict__
   pdl_trigger();
   extern __shared__ float sm[];       // a[C] = gamma*rstd, m1[C], m2[C], mean[C], rstd[C]
   float *s_a = sm, *s_m1 = sm + C, *s_m2 = sm + 2 * C, *s_mean = sm + 3 * C, *s_rstd = sm + 4 * C;
-  dp_exchange(xg, sums2, 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
+  dp_exchange(xg, const_cast<double*>(sums2), 2 * C, blockIdx.x == 0, threadIdx.x, blockDim.x, 0);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float rstd = save[C + c];
     // second statistic: sum g*xhat, or (fused dgrad epilogue) sum g*x which maps to it linearly

@@ -49,6 +49,11 @@ int k_bn_bwd_apply(const float* gm, const float* x, float* dx, const float* add,
                    float* dgamma, float* dbeta, float inv_world, int raw_x_sums, int tf32_round, cudaStream_t st,
                    DpXchg xg = DpXchg());
 
+// eval mode: (scale, shift) of every batch norm of a plan from its running statistics, one launch for all of them;
+// job i writes save[2C:3C] = gamma * rsqrt(rv + eps), save[3C:4C] = beta - rm * scale
+struct BnEvalJob { const float* gamma; const float* beta; const float* rm; const float* rv; size_t save_off; int C; };
+int k_bn_eval_coefs(const BnEvalJob* jobs_dev, int njobs, int max_c, float* save_base, cudaStream_t st);
+
 // ---- coupling pieces (modules_realnvp.py:264-302, 324-370) ------------------------
 int k_cpl_in_stats(const float* x, CplGeom g, double* sums, cudaStream_t st);
 int k_cpl_in_build(const float* x, CplGeom g, const double* sums, double count, const float* gamma,
@@ -197,6 +202,10 @@ struct ConvArgs {
   int round_out = 0;
   // tensor-core kernel only: x is the RAW pre-BN activation; relu(bn(x)) is applied to the staged operand tiles
   const BnPrologue* xf = nullptr;
+  // tensor-core kernel only, eval mode: y = relu(y * post_scale[n] + post_shift[n]) after bias / residual -- the batch
+  // norm (running statistics = a fixed affine map) + ReLU of the NEXT layer, folded into this conv's epilogue
+  const float* post_scale = nullptr;
+  const float* post_shift = nullptr;
   const CplEpilogue* cpl = nullptr;          // with xf only: the out conv of a coupling's s/t network
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);

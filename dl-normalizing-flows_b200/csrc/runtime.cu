@@ -119,6 +119,8 @@ struct rnvp_plan {
   int max_cout = 0;
   Seg* d_segs = nullptr;
   int nsegs = 0;
+  BnEvalJob* d_bnjobs = nullptr;     // every batch norm of the s/t nets (eval-mode coefficient table)
+  int n_bnjobs = 0, max_bn_c = 0;
   int math = RNVP_MATH_FP32;
   bool bound = false;
   bool single = false;               // one stand-alone coupling (rnvp_plan_create_single)
@@ -487,7 +489,8 @@ ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x,
 }
 
 int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S, float* y, int ldy,
-             const float* bias, const float* res, double* stats, bool operand_out = false) {
+             const float* bias, const float* res, double* stats, bool operand_out = false,
+             const float* post_save = nullptr /* (mean, rstd, scale, shift)[n] of the next layer's BN: eval fold */) {
   ProfScope ps(dgrad ? PROF_DGRAD : PROF_CONV, S, cv.taps, dgrad ? cv.cout : cv.cin, dgrad ? cv.cin : cv.cout, c.st);
   ConvArgs a{};
   a.x = x;
@@ -500,18 +503,20 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
   a.taps = cv.taps; a.ldy = ldy;
   // y is read raw by later conv MMAs: round it where it is produced (tensor-core tier only)
   a.round_out = operand_out && c.p->math == RNVP_MATH_TF32;
+  if (post_save) { a.post_scale = post_save + 2 * a.n; a.post_shift = post_save + 3 * a.n; }
   return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
 }
 // conv whose input is relu(bn_bi(x_raw)): BN prologue inside the tensor-core kernel
 int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, double count, const float* x_raw, int S,
                 float* y, int ldy, const float* bias, const float* res, double* stats, bool operand_out,
-                const CplEpilogue* cpl = nullptr) {
+                const CplEpilogue* cpl = nullptr, const float* post_save = nullptr) {
   rnvp_plan* p = c.p;
   const CouplingDesc& d = p->cpl[ci];
   const BnDesc& b = d.bns[bi];
   ProfScope ps(PROF_CONV, S, cv.taps, cv.cin, cv.cout, c.st);
   ConvArgs a = conv_args(c, cv, false, x_raw, S, y, ldy, bias, res, stats);
   a.round_out = operand_out;
+  if (post_save) { a.post_scale = post_save + 2 * a.n; a.post_shift = post_save + 3 * a.n; }
   BnPrologue x{};
   x.mode = training ? 1 : 0; x.C = b.C; x.sums = c.sf(b.sf); x.count = count;
   x.gamma = P_<float>(p, d, ci, b.slot_w); x.beta = P_<float>(p, d, ci, b.slot_b);
@@ -604,6 +609,19 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
   for (int i = 0; i < R; ++i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
     float *ai = c.act(ci, A.a[i]), *an = c.act(ci, A.a[i + 1]);
+    if (!training && xf) {
+      // eval mode: every BN is a fixed affine map (coefficients in `save`, eval_bn_coefs).  bn2 / bn3 + ReLU ride in the
+      // epilogue of the conv that PRODUCES their input (no other consumer needs u1 / u2 raw), bn1 in rb0's operand
+      // path: no bn_relu pass at all, and the 3x3 conv reads a ready-made operand.
+      float* h2 = Hs;                                   // scratch: the 3x3 conv cannot run in place on u1 == u2
+      float* h3 = c.act(ci, A.u2[i]);
+      RNVP_TRY(run_conv_bn(c, ci, *rb0, 3 * i, 0, count, ai, S, h2, ld, nullptr, nullptr, nullptr, true, nullptr,
+                           c.save(d.bns[3 * i + 1].save)));
+      RNVP_TRY(run_conv(c, *rb3, false, h2, S, h3, ld, nullptr, nullptr, nullptr, true, c.save(d.bns[3 * i + 2].save)));
+      RNVP_TRY(run_conv(c, *rb6, false, h3, S, an, ld, bias(*rb6), ai, nullptr, true));
+      RNVP_TRY(skip_conv(*cs, an, c.act(ci, A.skip), nullptr));
+      continue;
+    }
     RNVP_TRY(bn_conv(3 * i, ai, *rb0, c.act(ci, A.u1[i]), ld, nullptr, nullptr, st_of(3 * i + 1), false));
     RNVP_TRY(bn_conv(3 * i + 1, c.act(ci, A.u1[i]), *rb3, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2), false));
     RNVP_TRY(bn_conv(3 * i + 2, c.act(ci, A.u2[i]), *rb6, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr, true));
@@ -841,6 +859,10 @@ int materialize_weights(const Ctx& c, int first_job, int njobs) {
   return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(),
                           c.p->math == RNVP_MATH_TF32, c.st);
 }
+// eval mode: the batch norms are fixed affine maps; their (scale, shift) go into the `save` arena once per call
+int eval_bn_coefs(const Ctx& c) {
+  return k_bn_eval_coefs(c.p->d_bnjobs, c.p->n_bnjobs, c.p->max_bn_c, c.save(0), c.st);
+}
 
 int zero_pass(const Ctx& c, bool backward) {
   if (!backward) {
@@ -948,6 +970,7 @@ int rnvp_plan_destroy(rnvp_plan* p) {
   if (!p) return RNVP_OK;
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_segs) cudaFree(p->d_segs);
+  if (p->d_bnjobs) cudaFree(p->d_bnjobs);
   if (p->side) {
     cudaStreamSynchronize(p->side);
     cudaStreamDestroy(p->side);
@@ -1027,6 +1050,20 @@ int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* 
     for (auto& e : p->ev_done) RNVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RNVP_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   }
+  std::vector<BnEvalJob> bnjobs;
+  for (size_t ci = 0; ci < p->cpl.size(); ++ci) {
+    const CouplingDesc& d = p->cpl[ci];
+    size_t base = ci * p->slots_per_coupling;
+    for (const BnDesc& b : d.bns) {
+      bnjobs.push_back(BnEvalJob{(const float*)p->params[base + b.slot_w], (const float*)p->params[base + b.slot_b],
+                                 (const float*)p->params[base + b.slot_rm], (const float*)p->params[base + b.slot_rv],
+                                 b.save, b.C});
+      p->max_bn_c = std::max(p->max_bn_c, b.C);
+    }
+  }
+  if (!p->d_bnjobs) RNVP_CUDA(cudaMalloc(&p->d_bnjobs, bnjobs.size() * sizeof(BnEvalJob)));
+  RNVP_CUDA(cudaMemcpyAsync(p->d_bnjobs, bnjobs.data(), bnjobs.size() * sizeof(BnEvalJob), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  p->n_bnjobs = (int)bnjobs.size();
   if (!p->d_jobs) RNVP_CUDA(cudaMalloc(&p->d_jobs, jobs.size() * sizeof(WnJob)));
   if (!p->d_segs) RNVP_CUDA(cudaMalloc(&p->d_segs, segs.size() * sizeof(Seg)));
   RNVP_CUDA(cudaMemcpyAsync(p->d_jobs, jobs.data(), jobs.size() * sizeof(WnJob), cudaMemcpyHostToDevice, st));
@@ -1099,6 +1136,7 @@ int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logde
   if (training && p->world > 1) RNVP_TRY(dp_check_equal_batches(&p->dp, batch, c.ws_acc() + 8, c.st));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  if (!training) RNVP_TRY(eval_bn_coefs(c));
   if (weight_scale) {
     RNVP_TRY(k_sumsq(p->d_segs, p->nsegs, c.ws_acc(), c.st));
     RNVP_TRY(k_sumsq_finish(c.ws_acc(), weight_scale, c.st));
@@ -1221,6 +1259,7 @@ int rnvp_flow_inverse(rnvp_plan* p, const float* z_nchw, float* x_nchw, int batc
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   // factor_out chain (flow_realnvp.py:197-200): in_ckbd[s+1], off[s] = factor_out(in_ckbd[s])
   RNVP_TRY(k_nchw_to_nhwc(z_nchw, f.in_ckbd[1], batch, cf.channels, cf.image_size, cf.image_size, c.st));
@@ -1273,6 +1312,7 @@ int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nc
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   RNVP_TRY(k_nchw_to_nhwc(x_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
   RNVP_TRY(coupling_forward(c, ci, f.T[0], f.T[1], logJ_nchw ? f.G[0] : nullptr, training));
@@ -1294,6 +1334,7 @@ int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nc
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
   RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   RNVP_TRY(k_nchw_to_nhwc(y_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
   RNVP_TRY(coupling_inverse(c, ci, f.T[0], f.T[1], training, logJ_nchw ? f.G[0] : nullptr));

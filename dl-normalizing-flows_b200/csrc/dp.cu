@@ -181,10 +181,13 @@ int dp_sticky_error(const DpState* dp) {
 int dp_fused_exchange(DpState* dp, double* buf, size_t n, cudaStream_t st, DpXchg* out) {
   *out = DpXchg();
   if (dp->world <= 1) return RNVP_OK;
+  // Opt-in (RNVP_DP_FUSED=1).  Bit-exact, but measured SLOWER than the stand-alone exchange kernel at 2 GPUs (82.1 vs
+  // 77.0 ms per step, profiles/r02_scaling.md): while the single-CTA kernel waits for the peers the SMs are free for the
+  // wgrad side stream, whereas a consumer grid that waits in its prologue holds them.
   static int fused = -1;
   if (fused < 0) {
     const char* e = getenv("RNVP_DP_FUSED");
-    fused = (e && e[0] == '0') ? 0 : 1;
+    fused = (e && e[0] == '1') ? 1 : 0;
   }
   if (fused && dp->xchg_ready && (int)n <= dp->xchg_cap) {
     out->peers = dp->xchg_peers_dev;

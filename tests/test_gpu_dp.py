@@ -110,8 +110,11 @@ def _worker(rank, world, port, ret):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_equals_single_process():
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_two_rank_equals_single_process(fused, monkeypatch):
+    """fused = 1: the statistic exchange folded into the consumer kernels (RNVP_DP_FUSED, off by default)."""
     import torch.multiprocessing as mp
+    monkeypatch.setenv("RNVP_DP_FUSED", fused)
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
     port = _free_port()

@@ -20,6 +20,7 @@ for s in $STEPS; do
     dptest) timeout 1200 python -m pytest tests/test_gpu_dp.py -m gpu -q --timeout 900 > $OUT/${TAG}_dptest.log 2>&1; echo "dptest rc=$?" ;;
     weak) run weak "NCCL_DEBUG=INFO" --steps 10 --warmup 3 --no-cpu-baseline ;;
     weak_plain) run weak_plain "A=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
+    weak_fused) run weak_fused "RNVP_DP_FUSED=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
     weak_nofused) run weak_nofused "RNVP_DP_FUSED=0" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
     strong) run strong "A=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof --global-batch 2048 ;;
     sample_strong) run sample_strong "A=1" --mode sample --steps 5 --warmup 3 --no-cpu-baseline --no-prof --global-batch 4096 ;;

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(CT) conv_fwd_fp32_kernel(ConvArgs a) {
     const bool pv = tap_pixel(m0 + lr, a.S, tap, a.taps, P, &src);
     const float* xrow = a.x + src * a.kpad;
     const int nrow = n0 + lr;
-    const float* wrow = a.w + ((int64_t)tap * a.npad + nrow) * a.kpad;
+    const float* wrow = a.w + ((int64_t)tap * a.npad + nrow) * (a.ldw ? a.ldw : a.kpad);
     const bool nv = nrow < a.npad;
     for (int k0 = 0; k0 < a.kpad; k0 += BK) {
       float4 av = pv ? *reinterpret_cast<const float4*>(xrow + k0 + lq * 4) : make_float4(0, 0, 0, 0);
@@ -110,6 +110,7 @@ int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(a.kpad % BK == 0, "conv: kpad=%d must be a multiple of %d", a.kpad, BK);
   RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "conv: taps=%d", a.taps);
+  RNVP_REQUIRE(a.segs == 1, "the CUDA-core conv takes one input tensor (the runtime loops over K segments)");
   static_assert(sizeof(float) * BK * (BM + 4) >= sizeof(float) * 16 * BN, "stats scratch");
   dim3 grid(ceil_div(P, BM), ceil_div(a.n, BN));
   conv_fwd_fp32_kernel<<<grid, CT, 0, st>>>(a);
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(CT) conv_wgrad_fp32_kernel(WgradArgs a, int nt
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int k = k0 + tx * 4 + j;
-      if (k < a.kpad) atomicAdd(&a.dw[((int64_t)tap * a.npad + n) * a.kpad + k], acc[i][j]);
+      if (k < a.kpad) atomicAdd(&a.dw[((int64_t)tap * a.npad + n) * (a.lddw ? a.lddw : a.kpad) + k], acc[i][j]);
     }
   }
   if (do_bias && t < BN && n0 + t < a.n) atomicAdd(&a.dbias[n0 + t], bsum);
@@ -185,6 +186,7 @@ int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st) {
   const int P = a.B * a.S * a.S;
   if (P == 0) return RNVP_OK;
   RNVP_REQUIRE(a.kpad % 4 == 0 && a.lddy % 4 == 0, "wgrad: strides must be multiples of 4");
+  RNVP_REQUIRE(a.segs == 1, "the CUDA-core wgrad takes one input tensor (the runtime loops over K segments)");
   int ntiles = ceil_div(a.n, BN), ktiles = ceil_div(a.kpad, BN);
   int base = ntiles * ktiles * a.taps;
   int splits = ceil_div(kNumSMs * 4, base);

@@ -68,6 +68,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -239,7 +244,8 @@ struct ConvTcParams {
   int round_out;                     // round the result to TF32 (cvt.rna): it is the raw operand of another conv MMA
   const float* post_scale;           // eval mode: y = relu(y * post_scale[n] + post_shift[n]) -- the NEXT layer's batch
   const float* post_shift;           //   norm (fixed affine on running statistics) + ReLU applied where y is produced
-  int P, n, taps, kchunks;           // kchunks = kpad / 32
+  int P, n, taps, kchunks;           // kchunks = segs * kpad / 32
+  int segs, kps;                     // K-concatenated input: `segs` tensors of kps 32-channel chunks each (tmA's 5th dimension)
   int S, log2S;
   int m_tiles, n_tiles;
   int stages;                        // depth of the smem ring (<= TC_MAX_STAGES)
@@ -386,13 +392,16 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int tap = 0; tap < prm.taps; ++tap) {
           int dy = 0, dx = 0;
           if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-          for (int kc = 0; kc < prm.kchunks; ++kc) {
-            mbar_wait(&empty_bar[s], ph);
-            uint8_t* a_dst = smem + s * STAGE_BYTES;
-            mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-            tma_load_4d(a_dst, &tmA, &full_bar[s], kc * 32, col0 + dx, row0 + dy, img0);
-            tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+          int kc = 0;
+          for (int seg = 0; seg < prm.segs; ++seg) {
+            for (int kk = 0; kk < prm.kps; ++kk, ++kc) {
+              mbar_wait(&empty_bar[s], ph);
+              uint8_t* a_dst = smem + s * STAGE_BYTES;
+              mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+              tma_load_5d(a_dst, &tmA, &full_bar[s], kk * 32, col0 + dx, row0 + dy, img0, seg);
+              tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
           }
         }
       }
@@ -847,13 +856,14 @@ static bool pixel_box(int S, int npix, int* bw, int* bh, int* bn) {
   return (*bw) * (*bh) * (*bn) == npix && *bn <= 256;
 }
 
-// activation map over x [B][S][S][ld] fp32 with a (32, bw, bh, bn) box
+// activation map over `segs` tensors x_i [B][S][S][ld] fp32 lying seg_stride floats apart, with a (32, bw, bh, bn, 1) box
 static int make_act_map(CUtensorMap* m, const float* x, int B, int S, int ld, int bw, int bh, int bn,
-                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
-  cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4};
-  cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  return encode_map(m, x, 4, dims, strides, box, swz);
+                        CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, int segs = 1, size_t seg_stride = 0) {
+  if (segs <= 1) { segs = 1; seg_stride = (size_t)B * S * S * ld; }
+  cuuint64_t dims[5] = {(cuuint64_t)ld, (cuuint64_t)S, (cuuint64_t)S, (cuuint64_t)B, (cuuint64_t)segs};
+  cuuint64_t strides[4] = {(cuuint64_t)ld * 4, (cuuint64_t)S * ld * 4, (cuuint64_t)S * S * ld * 4, (cuuint64_t)seg_stride * 4};
+  cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, 1};
+  return encode_map(m, x, 5, dims, strides, box, swz);
 }
 
 bool tf32_supported(int S) {
@@ -908,9 +918,10 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   CUtensorMap tmA, tmB, tmY, tmR;
   int bw = 0, bh = 0, bn = 0;
   pixel_box(a.S, 128, &bw, &bh, &bn);
-  RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn));
-  cuuint64_t dims[3] = {(cuuint64_t)a.kpad, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
-  cuuint64_t strides[2] = {(cuuint64_t)a.kpad * 4, (cuuint64_t)a.npad * a.kpad * 4};
+  RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B, a.segs, a.seg_stride));
+  const int ktot = a.segs * a.kpad, ldw = a.ldw ? a.ldw : ktot;
+  cuuint64_t dims[3] = {(cuuint64_t)ktot, (cuuint64_t)a.npad, (cuuint64_t)a.taps};
+  cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)a.npad * ldw * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
   const float* rsrc = a.bn_x ? a.bn_x : a.res;
@@ -970,8 +981,8 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   if (P == 0) return RNVP_OK;
   int bw, bh, bn;
   if (!pixel_box(a.S, 128, &bw, &bh, &bn) || a.kpad % 32 != 0 || a.ldy % 4 != 0) {
-    RNVP_REQUIRE(a.bn_x == nullptr && a.xf == nullptr && a.post_scale == nullptr,
-                 "fused BN prologue / epilogues need the tensor-core kernel");
+    RNVP_REQUIRE(a.bn_x == nullptr && a.xf == nullptr && a.post_scale == nullptr && a.segs == 1,
+                 "fused BN prologue / epilogues / K-concatenated inputs need the tensor-core kernel");
     return k_conv_fwd_fp32(a, st);          // shapes the TMA box cannot express: CUDA-core kernel
   }
   RNVP_REQUIRE(a.bn_x == nullptr || (a.res == nullptr && a.bias == nullptr && a.n % 4 == 0 && a.bn_save && a.stats),
@@ -986,7 +997,10 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   RNVP_REQUIRE((a.post_scale == nullptr) == (a.post_shift == nullptr) && (a.post_scale == nullptr || (a.n % 4 == 0 && a.bn_x == nullptr)),
                "conv: the post-affine epilogue needs scale and shift, n % 4 == 0 and no fused BN backward");
   prm.post_scale = a.post_scale; prm.post_shift = a.post_shift;
-  prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.kpad / 32;
+  RNVP_REQUIRE(a.segs >= 1 && (a.segs == 1 || (a.xf == nullptr && a.seg_stride % 4 == 0 && (a.ldw == 0 || a.ldw % 4 == 0))),
+               "conv: K-concatenated input needs 16-byte aligned segments and excludes the BN prologue");
+  prm.P = P; prm.n = a.n; prm.taps = a.taps; prm.kchunks = a.segs * (a.kpad / 32);
+  prm.segs = a.segs; prm.kps = a.kpad / 32;
   prm.S = a.S;
   prm.log2S = 0;
   while ((1 << prm.log2S) < a.S) ++prm.log2S;
@@ -1043,7 +1057,8 @@ constexpr int WG_MAX_GROUPS = 16;
 struct WgradTcParams {
   float* dw;
   float* dbias;
-  int P, n, npad, kpad, taps, S;
+  int P, n, npad, kpad, taps, S;            // kpad = segs * seg_k (all input channels of the K-concatenated x)
+  int seg_k, lddw;                          // channels per x tensor (tmX's 5th dimension picks the tensor); row stride of dw
   int n_tiles, k_tiles, tap_ranges, taps_per_range;
   int kb;                                   // x boxes (32 channels) per tap inside a k-tile (full tiles)
   int tpm;                                  // taps packed into one M = 128 operand
@@ -1132,12 +1147,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
         int img0 = p0 / hw, rem = p0 % hw;
         int as = 0, bs = 0;
         uint32_t aph = 1, bph = 1;                        // parity of the "slot free" waits (first pass: free)
+        int xch[4], xseg[4];                              // channel offset / tensor of x box j (K-concatenated x)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { xseg[j] = (k0 + 32 * j) / prm.seg_k; xch[j] = (k0 + 32 * j) % prm.seg_k; }
         for (int t = t_begin; t < t_end; ++t) {
           const int row0 = rem / prm.S, col0 = rem % prm.S;
           mbar_wait(&b_empty[bs], bph);
           mbar_expect_tx(&b_full[bs], nbx * WG_BOX_BYTES);
           for (int g = 0; g < nbx; ++g)
-            tma_load_4d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &b_full[bs], n0 + 32 * g, col0, row0, img0);
+            tma_load_5d(b_ring + bs * WG_B_STAGE_BYTES + g * WG_BOX_BYTES, &tmDy, &b_full[bs], n0 + 32 * g, col0, row0, img0, 0);
           if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1; }
           for (int mg = 0; mg < groups; ++mg) {
             const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);       // taps in this M-group
@@ -1147,9 +1165,11 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
               const int tap = tap0 + mg * prm.tpm + tl;
               int dy = 0, dx = 0;
               if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-              for (int j = 0; j < kb; ++j)
-                tma_load_4d(a_ring + as * WG_A_STAGE_BYTES + (tl * kb + j) * WG_BOX_BYTES, &tmX, &a_full[as],
-                            k0 + 32 * j, col0 + dx, row0 + dy, img0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < kb)
+                  tma_load_5d(a_ring + as * WG_A_STAGE_BYTES + (tl * kb + j) * WG_BOX_BYTES, &tmX, &a_full[as],
+                              xch[j], col0 + dx, row0 + dy, img0, xseg[j]);
             }
             if (++as == WG_A_STAGES) { as = 0; aph ^= 1; }
           }
@@ -1286,14 +1306,14 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       for (int mg = 0; mg < groups; ++mg) {
         const int tap_l = mg * prm.tpm + tl;
         const bool rvalid = tl < prm.tpm && tap_l < ntap;
-        float* dst = prm.dw + ((int64_t)(tap0 + tap_l) * prm.npad + n0) * prm.kpad + k0 + k;
+        float* dst = prm.dw + ((int64_t)(tap0 + tap_l) * prm.npad + n0) * prm.lddw + k0 + k;
         for (int c0 = 0; c0 < N; c0 += 32) {
           float v[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mg * N + c0), v);
           if (rvalid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (n0 + c0 + j < prm.n) atomicAdd(dst + (int64_t)(c0 + j) * prm.kpad, v[j]);
+              if (n0 + c0 + j < prm.n) atomicAdd(dst + (int64_t)(c0 + j) * prm.lddw, v[j]);
           }
         }
       }
@@ -1321,16 +1341,20 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   CUtensorMap tmDy, tmX;
   // MN-major fp32 operands: 128B swizzle with 32-byte atoms (the only layout tcgen05 accepts for them)
   RNVP_TRY(make_act_map(&tmDy, a.dy, a.B, a.S, a.lddy, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  RNVP_TRY(make_act_map(&tmX, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  RNVP_TRY(make_act_map(&tmX, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, a.segs, a.seg_stride));
+  RNVP_REQUIRE(a.segs >= 1 && (a.segs == 1 || (a.xf_save == nullptr && a.seg_stride % 4 == 0)),
+               "wgrad: K-concatenated x needs 16-byte aligned segments and excludes the BN prologue");
+  const int ktot = a.segs * a.kpad;
   WgradTcParams prm{};
   prm.dw = a.dw; prm.dbias = a.dbias;
-  prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = a.kpad; prm.taps = a.taps; prm.S = a.S;
+  prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = ktot; prm.taps = a.taps; prm.S = a.S;
+  prm.seg_k = a.kpad; prm.lddw = a.lddw ? a.lddw : ktot;
   prm.xf_save = a.xf_save; prm.xf_C = a.xf_C;
   prm.log2S = 0;
   while ((1 << prm.log2S) < a.S) ++prm.log2S;
   prm.n_tiles = ceil_div(a.n, 128);
-  prm.k_tiles = ceil_div(a.kpad, 128);
-  prm.kb = (a.kpad < 128 ? a.kpad : 128) / 32;
+  prm.k_tiles = ceil_div(ktot, 128);
+  prm.kb = (ktot < 128 ? ktot : 128) / 32;
   prm.tpm = prm.kb == 3 ? 1 : 4 / prm.kb;
   if (prm.tpm > a.taps) prm.tpm = a.taps;
   const int N = pad_to(a.n < 128 ? a.n : 128, 32);

@@ -1141,6 +1141,7 @@ __global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __rest
   }
   float* wf = wbase + j.wf_off;
   float* wb = wbase + j.wb_off;
+  const int ldf = j.ld_f ? j.ld_f : j.kpad_f;     // row stride of wf (a skip conv is a column block of a wider matrix)
   for (int ci0 = 0; ci0 < j.kpad_f; ci0 += kWnTile) {
     __syncthreads();                             // f ready / previous slab consumed
     const int ncols = min(kWnTile, j.cin - ci0) * taps;            // real floats per row in this slab (<= 0: none)
@@ -1156,7 +1157,7 @@ __global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __rest
       for (int r = warp; r < kWnTile; r += 8) {
         const int co = co0 + r;
         if (co < j.npad_f)
-          wf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci0 + lane] = maybe_round(slab[r * pitch + lane * taps + tap] * f[r], rnd);
+          wf[((int64_t)tap * j.npad_f + co) * ldf + ci0 + lane] = maybe_round(slab[r * pitch + lane * taps + tap] * f[r], rnd);
       }
       // wb[taps-1-tap][ci0 + i][co0 + lane]
       for (int i = warp; i < kWnTile; i += 8) {
@@ -1177,6 +1178,21 @@ int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbas
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
+// bias of the fused skip conv: sum of the biases of in_skip and the core_skips (one block per coupling)
+__global__ void bias_sum_kernel(const BiasSumJob* __restrict__ jobs, float* __restrict__ wbase) {
+  const BiasSumJob& j = jobs[blockIdx.x];
+  for (int c = threadIdx.x; c < j.C; c += blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < j.n; ++i) s += j.b[i][c];
+    wbase[j.out_off + c] = s;
+  }
+}
+int k_bias_sum(const BiasSumJob* jobs_dev, int njobs, float* wbase, cudaStream_t st) {
+  if (njobs == 0) return RNVP_OK;
+  bias_sum_kernel<<<njobs, 256, 0, st>>>(jobs_dev, wbase);
+  RNVP_LAUNCH_CHECK();
+  return RNVP_OK;
+}
 // dg = sum dw * v/||v|| ; dv = (g/||v||) * (dw - dg * v/||v||)
 __global__ void weightnorm_bwd_kernel(const WnJob* __restrict__ jobs, const float* __restrict__ dwbase) {
   pdl_wait();
@@ -1188,12 +1204,14 @@ __global__ void weightnorm_bwd_kernel(const WnJob* __restrict__ jobs, const floa
   int per = j.cin * j.taps;
   const float* v = j.v + (int64_t)co * per;
   const float* dwf = dwbase + j.dw_off;
+  const int lddw = j.ld_dw ? j.ld_dw : j.kpad_f;
+  if (j.dbias && threadIdx.x == 0) j.dbias[co] += dwbase[j.dbias_src_off + co];
   float ss = 0.f, dot = 0.f;
   for (int e = threadIdx.x; e < per; e += blockDim.x) {
     int ci = e / j.taps, tap = e % j.taps;
     float vv = v[e];
     ss += vv * vv;
-    dot += vv * dwf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci];
+    dot += vv * dwf[((int64_t)tap * j.npad_f + co) * lddw + ci];
   }
   ss = block_sum(ss, sm);
   dot = block_sum(dot, sm);
@@ -1205,7 +1223,7 @@ __global__ void weightnorm_bwd_kernel(const WnJob* __restrict__ jobs, const floa
   float* dv = j.dv + (int64_t)co * per;
   for (int e = threadIdx.x; e < per; e += blockDim.x) {
     int ci = e / j.taps, tap = e % j.taps;
-    float dw = dwf[((int64_t)tap * j.npad_f + co) * j.kpad_f + ci];
+    float dw = dwf[((int64_t)tap * j.npad_f + co) * lddw + ci];
     dv[e] += gi * (dw - dg * v[e] * inv);
   }
 }

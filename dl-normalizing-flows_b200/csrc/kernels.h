@@ -103,12 +103,25 @@ struct WnJob {
   size_t dw_off;       // wgrad output, same layout as wf
   int cout, cin, taps;
   int npad_f, kpad_f, npad_b, kpad_b;
+  // Row strides (floats) of wf and of the wgrad output; 0 = kpad_f.  The skip convs of a coupling (in_skip,
+  // core_skips) are column blocks of ONE [npad][(R+1)*ldD] matrix: their sum over the trunk tensors is a single
+  // GEMM with the K dimension concatenated (runtime.cu, skip_fused).
+  int ld_f, ld_dw;
+  // bias gradient that the fused skip wgrad left in the wgrad scratch (it is the same vector for every skip conv):
+  // dbias[co] += dwbase[dbias_src_off + co] when dbias != null
+  float* dbias;
+  size_t dbias_src_off;
 };
 // writes every element of wf and wb (zero in the padding), so the arena needs no clearing
 int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
                      cudaStream_t st);
 int k_weightnorm_bwd(const WnJob* jobs_dev, int njobs, int max_cout, const float* wbase,
                      const float* dwbase, cudaStream_t st);
+
+// out[wbase + out_off + c] = sum_i b[i][c]: the bias of the fused skip conv (one launch for all couplings)
+constexpr int kMaxSkipConvs = 17;
+struct BiasSumJob { const float* b[kMaxSkipConvs]; int n; int C; size_t out_off; };
+int k_bias_sum(const BiasSumJob* jobs_dev, int njobs, float* wbase, cudaStream_t st);
 
 struct Seg { const float* p; float* g; int n; };
 int k_sumsq(const Seg* segs_dev, int nsegs, double* acc, cudaStream_t st);      // acc += sum p^2
@@ -207,6 +220,11 @@ struct ConvArgs {
   const float* post_scale = nullptr;
   const float* post_shift = nullptr;
   const CplEpilogue* cpl = nullptr;          // with xf only: the out conv of a coupling's s/t network
+  // K-concatenated input: x is `segs` tensors [B,S,S,kpad] lying `seg_stride` floats apart, w has segs*kpad columns
+  // (y = sum_i conv(x_i, w[:, i*kpad:(i+1)*kpad])); ldw = row stride of w in floats (0 = segs*kpad)
+  int segs = 1;
+  size_t seg_stride = 0;
+  int ldw = 0;
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
@@ -222,6 +240,10 @@ struct WgradArgs {
   // to tf32(relu(x * scale + shift)) in shared memory with (mean, rstd, scale, shift)[xf_C] = xf_save
   const float* xf_save = nullptr;
   int xf_C = 0;
+  // K-concatenated x (see ConvArgs): dw has segs*kpad columns; lddw = row stride of dw in floats (0 = segs*kpad)
+  int segs = 1;
+  size_t seg_stride = 0;
+  int lddw = 0;
 };
 bool wgrad_tf32_prologue_ok(const WgradArgs& a);
 int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st);

@@ -48,10 +48,12 @@ namespace {
 struct ConvDesc {
   int cin, cout, taps;
   bool has_bias, train_g;
+  bool is_skip;          // in_skip / core_skips: a column block of the coupling's fused skip matrix
   int kpad, npad;        // forward operand  wf [taps][npad][kpad]
   int kpad_b, npad_b;    // dgrad operand    wb [taps][npad_b][kpad_b]
   size_t wf_off, wb_off; // float offsets inside the weight arena
   size_t dw_off;         // float offset inside the per-coupling wgrad scratch
+  int ld_f, ld_dw;       // row strides of wf / dw in floats (skip convs: column blocks of the fused skip matrix)
   int slot_v, slot_g, slot_bias;   // slots relative to the coupling
 };
 struct BnDesc {
@@ -70,6 +72,10 @@ struct CouplingDesc {
   size_t save_in, save_out;              // float offsets
   int job0;                              // first weight-norm job
   size_t dw_floats;                      // wgrad scratch this coupling needs
+  // fused skip path: skip = sum_i skip_conv_i(a_i) is ONE 1x1 conv over the K-concatenated trunk tensors a_0..a_R
+  // with the weight matrix wskip [npad][(R+1)*ldD] (every skip conv's wf is a column block of it)
+  size_t wskip_off, bskip_off;           // weight arena: the matrix, the summed bias [ldD]
+  size_t dwskip_off, dbskip_off;         // wgrad scratch: its gradient, the (shared) bias gradient [ldD]
   CplGeom geom(int B) const {
     CplGeom g;
     g.B = B; g.S = S; g.C = C; g.cio = cio;
@@ -119,6 +125,7 @@ struct rnvp_plan {
   int max_cout = 0;
   Seg* d_segs = nullptr;
   int nsegs = 0;
+  BiasSumJob* d_biasjobs = nullptr;  // one per coupling: the summed bias of the fused skip conv
   BnEvalJob* d_bnjobs = nullptr;     // every batch norm of the s/t nets (eval-mode coefficient table)
   int n_bnjobs = 0, max_bn_c = 0;
   int math = RNVP_MATH_FP32;
@@ -256,10 +263,28 @@ int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
     RNVP_REQUIRE(d.ldD / 4 <= 256, "coupling %s: D=%d unsupported (max 1024)", d.name.c_str(), d.D);
     d.job0 = job;
     size_t dwo = 0;
-    for (auto& cv : d.convs) {
-      cv.wf_off = wo; wo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
+    const int nskip = R + 1, ldskip = nskip * d.ldD;
+    const size_t skip_floats = align_up((size_t)d.convs[1].npad * ldskip, 64);
+    d.wskip_off = wo; wo += skip_floats;
+    d.bskip_off = wo; wo += align_up((size_t)d.ldD, 64);
+    d.dwskip_off = dwo; dwo += skip_floats;
+    d.dbskip_off = dwo; dwo += align_up((size_t)d.ldD, 64);
+    int si = 0;
+    for (size_t k = 0; k < d.convs.size(); ++k) {
+      ConvDesc& cv = d.convs[k];
+      const bool is_skip = k == 1 || (k >= 2 && k < d.convs.size() - 1 && (k - 2) % 4 == 3);
+      cv.is_skip = is_skip;
+      if (is_skip) {                       // column block si of the fused skip matrix
+        cv.wf_off = d.wskip_off + (size_t)si * d.ldD;
+        cv.dw_off = d.dwskip_off + (size_t)si * d.ldD;
+        cv.ld_f = cv.ld_dw = ldskip;
+        ++si;
+      } else {
+        cv.wf_off = wo; wo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
+        cv.dw_off = dwo; dwo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
+        cv.ld_f = cv.ld_dw = cv.kpad;
+      }
       cv.wb_off = wo; wo += align_up((size_t)cv.taps * cv.npad_b * cv.kpad_b, 64);
-      cv.dw_off = dwo; dwo += align_up((size_t)cv.taps * cv.npad * cv.kpad, 64);
       p->max_cout = std::max(p->max_cout, cv.cout);
       ++job;
     }
@@ -300,9 +325,9 @@ CplAct cpl_act(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
   if (mode >= 1) {
     for (int i = 0; i <= R; ++i) a.a[i] = take(Pn * d.ldD);
     for (int i = 0; i < R; ++i) { a.u1[i] = take(Pn * d.ldD); a.u2[i] = take(Pn * d.ldD); }
-  } else {                               // inference: the trunk is updated in place
-    size_t aa = take(Pn * d.ldD), uu = take(Pn * d.ldD);
-    for (int i = 0; i <= R; ++i) a.a[i] = aa;
+  } else {                               // inference: u1 / u2 are one scratch buffer; the trunk tensors a_0..a_R stay
+    for (int i = 0; i <= R; ++i) a.a[i] = take(Pn * d.ldD);   // (the fused skip conv reads all of them at the end)
+    size_t uu = take(Pn * d.ldD);
     for (int i = 0; i < R; ++i) { a.u1[i] = uu; a.u2[i] = uu; }
   }
   a.skip = take(Pn * d.ldD);
@@ -429,6 +454,25 @@ bool bn_fused(const rnvp_plan* p, const CouplingDesc& d, int bi) {
   return consumer_1x1 && cpl_xf(p, d);
 }
 
+// The skip path as ONE conv: skip = sum_i skip_conv_i(a_i) = [a_0 | ... | a_R] x wskip, a 1x1 conv whose K dimension
+// runs over the R+1 trunk tensors (a fifth TMA dimension), instead of R+1 launches that each read and re-write the
+// running sum: 6 instead of 14 trunk-sized HBM passes per coupling, 4 launches fewer.  Its wgrad is likewise one
+// launch over the concatenated x.  Tensor-core tier only; RNVP_SKIP_FUSED=0 restores the separate convs (A/B).
+bool skip_fused(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("RNVP_SKIP_FUSED");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!on || p->math != RNVP_MATH_TF32) return false;
+  ConvArgs a{};
+  a.S = d.S; a.kpad = d.ldD; a.ldy = d.ldD; a.n = d.D;
+  WgradArgs w{};
+  w.S = d.S; w.kpad = d.ldD; w.lddy = d.ldD;
+  CplAct A = cpl_act(p, d, B, mode);
+  return conv_tf32_fusable(a) && wgrad_tf32_prologue_ok(w) && (A.a[1] - A.a[0]) % 4 == 0;
+}
+
 // the affine coupling map computed in the epilogue of the s/t net's out conv (needs the BN-prologue kernel);
 // RNVP_CPL_EPILOGUE=0 restores the separate cpl_fwd_a / cpl_inv passes (A/B measurements)
 bool cpl_fused(const rnvp_plan* p, const CouplingDesc& d) {
@@ -485,6 +529,7 @@ ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x,
   a.n = dgrad ? cv.cin : cv.cout;
   a.npad = dgrad ? cv.npad_b : cv.npad;
   a.taps = cv.taps; a.ldy = ldy;
+  a.ldw = dgrad ? cv.kpad_b : cv.ld_f;
   return a;
 }
 
@@ -492,15 +537,7 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
              const float* bias, const float* res, double* stats, bool operand_out = false,
              const float* post_save = nullptr /* (mean, rstd, scale, shift)[n] of the next layer's BN: eval fold */) {
   ProfScope ps(dgrad ? PROF_DGRAD : PROF_CONV, S, cv.taps, dgrad ? cv.cout : cv.cin, dgrad ? cv.cin : cv.cout, c.st);
-  ConvArgs a{};
-  a.x = x;
-  a.w = c.weights() + (dgrad ? cv.wb_off : cv.wf_off);
-  a.bias = bias; a.res = res; a.y = y; a.stats = stats;
-  a.B = c.B; a.S = S;
-  a.kpad = dgrad ? cv.kpad_b : cv.kpad;
-  a.n = dgrad ? cv.cin : cv.cout;
-  a.npad = dgrad ? cv.npad_b : cv.npad;
-  a.taps = cv.taps; a.ldy = ldy;
+  ConvArgs a = conv_args(c, cv, dgrad, x, S, y, ldy, bias, res, stats);
   // y is read raw by later conv MMAs: round it where it is produced (tensor-core tier only)
   a.round_out = operand_out && c.p->math == RNVP_MATH_TF32;
   if (post_save) { a.post_scale = post_save + 2 * a.n; a.post_shift = post_save + 3 * a.n; }
@@ -555,6 +592,7 @@ int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy,
   a.x = x; a.dy = dy; a.dw = c.dw() + cv.dw_off; a.dbias = dbias;
   a.xf_save = xf_save; a.xf_C = xf_C;
   a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
+  a.lddw = cv.ld_dw;
   return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.wst) : k_conv_wgrad_fp32(a, c.wst);
 }
 
@@ -596,7 +634,9 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
   // The skip path (in_skip and the core_skips, accumulated into `skip`) is off the critical chain of the
   // trunk: with the side stream active (training mode 2, every a_i has its own buffer) those five convs
   // overlap the residual blocks and are joined before out_block's batch norm.
+  const bool sfused = skip_fused(p, d, c.B, c.mode);
   auto skip_conv = [&](const ConvDesc& cvs, const float* x, const float* res, double* stats) -> int {
+    if (sfused) return RNVP_OK;              // one K-concatenated conv after the last block
     if (!c.side_on) return run_conv(c, cvs, false, x, S, c.act(ci, A.skip), ld, bias(cvs), res, stats);
     RNVP_TRY(fork_to_side(c));
     Ctx cs2 = c;
@@ -626,6 +666,14 @@ int net_forward(const Ctx& c, int ci, int training, const CplEpilogue* cpl = nul
     RNVP_TRY(bn_conv(3 * i + 1, c.act(ci, A.u1[i]), *rb3, c.act(ci, A.u2[i]), ld, nullptr, nullptr, st_of(3 * i + 2), false));
     RNVP_TRY(bn_conv(3 * i + 2, c.act(ci, A.u2[i]), *rb6, an, ld, bias(*rb6), ai, i + 1 < R ? st_of(3 * (i + 1)) : nullptr, true));
     RNVP_TRY(skip_conv(*cs, an, c.act(ci, A.skip), i == R - 1 ? st_of(3 * R) : nullptr));
+  }
+  if (sfused) {
+    ProfScope ps(PROF_CONV, S, 1, (R + 1) * d.D, d.D, c.st);
+    ConvArgs a = conv_args(c, cv[1], false, c.act(ci, A.a[0]), S, c.act(ci, A.skip), ld, c.weights() + d.bskip_off, nullptr,
+                           st_of(3 * R));
+    a.w = c.weights() + d.wskip_off;
+    a.segs = R + 1; a.seg_stride = A.a[1] - A.a[0]; a.ldw = (R + 1) * ld;
+    RNVP_TRY(k_conv_fwd_tf32(a, c.st));
   }
   RNVP_TRY(join_side(c));
   const ConvDesc& oc = cv[2 + 4 * R];
@@ -707,6 +755,18 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     RNVP_TRY(wgrad_bn(oc, 3 * R, c.act(ci, A.skip), dst, d.cst_pad, gbias(oc)));
     RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, G0, c.act(ci, A.skip), DO, nullptr, true));
   }
+  const bool sfused = skip_fused(p, d, c.B, c.mode);
+  if (sfused) {
+    // all R+1 skip wgrads in one launch: dw[n][(i, k)] = sum_p DO[p,n] * a_i[p,k]; the bias gradient (the same column
+    // sums of DO for every skip conv) goes to the scratch and is added to each bias by the weight-norm backward
+    RNVP_TRY(fork_to_side(c));
+    ProfScope ps(PROF_WGRAD, S, 1, (R + 1) * d.D, d.D, c.wst);
+    WgradArgs a{};
+    a.x = c.act(ci, A.a[0]); a.dy = DO; a.dw = c.dw() + d.dwskip_off; a.dbias = c.dw() + d.dbskip_off;
+    a.B = c.B; a.S = S; a.kpad = ld; a.n = d.D; a.npad = cv[1].npad; a.taps = 1; a.lddy = ld;
+    a.segs = R + 1; a.seg_stride = A.a[1] - A.a[0]; a.lddw = (R + 1) * ld;
+    RNVP_TRY(k_conv_wgrad_tf32(a, c.wst));
+  }
   const float* DA = nullptr;               // d(a_{i+1}) accumulated so far
   for (int i = R - 1; i >= 0; --i) {
     const ConvDesc *rb0 = &cv[2 + 4 * i], *rb3 = rb0 + 1, *rb6 = rb0 + 2, *cs = rb0 + 3;
@@ -714,7 +774,7 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     float *u1 = c.act(ci, A.u1[i]), *u2 = c.act(ci, A.u2[i]);
     // skip += core_skip_i(a_{i+1})
     float* DAc = take(3);
-    RNVP_TRY(run_wgrad(c, *cs, an, DO, ld, S, gbias(*cs)));
+    if (!sfused) RNVP_TRY(run_wgrad(c, *cs, an, DO, ld, S, gbias(*cs)));
     RNVP_TRY(run_conv(c, *cs, true, DO, S, DAc, ld, nullptr, DA, nullptr, true));
     // a_{i+1} = a_i + rb6(relu(bn3(u2)))
     float* G3 = take(1);
@@ -736,7 +796,7 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   }
   // skip = in_skip(a0) (+...); a0 = in_block(h0)
   float* DAf = take(3);
-  RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));
+  if (!sfused) RNVP_TRY(run_wgrad(c, cv[1], c.act(ci, A.a[0]), DO, ld, S, gbias(cv[1])));
   RNVP_TRY(run_conv(c, cv[1], true, DO, S, DAf, ld, nullptr, DA, nullptr, true));
   RNVP_TRY(run_wgrad(c, cv[0], c.act(ci, A.h0), DAf, ld, S, gbias(cv[0])));
   RNVP_TRY(run_conv(c, cv[0], true, DAf, S, dh0, d.cin_pad, nullptr, nullptr, nullptr));
@@ -855,7 +915,9 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
   return RNVP_OK;
 }
 
-int materialize_weights(const Ctx& c, int first_job, int njobs) {
+// first_cpl / ncpl: the couplings whose weights are (re)built (all of them for the flow, one for a stand-alone coupling)
+int materialize_weights(const Ctx& c, int first_job, int njobs, int first_cpl, int ncpl) {
+  RNVP_TRY(k_bias_sum(c.p->d_biasjobs + first_cpl, ncpl, c.weights(), c.st));
   return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(),
                           c.p->math == RNVP_MATH_TF32, c.st);
 }
@@ -971,6 +1033,7 @@ int rnvp_plan_destroy(rnvp_plan* p) {
   if (p->d_jobs) cudaFree(p->d_jobs);
   if (p->d_segs) cudaFree(p->d_segs);
   if (p->d_bnjobs) cudaFree(p->d_bnjobs);
+  if (p->d_biasjobs) cudaFree(p->d_biasjobs);
   if (p->side) {
     cudaStreamSynchronize(p->side);
     cudaStreamDestroy(p->side);
@@ -1037,6 +1100,11 @@ int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* 
       j.wf_off = cv.wf_off; j.wb_off = cv.wb_off; j.dw_off = cv.dw_off;
       j.cout = cv.cout; j.cin = cv.cin; j.taps = cv.taps;
       j.npad_f = cv.npad; j.kpad_f = cv.kpad; j.npad_b = cv.npad_b; j.kpad_b = cv.kpad_b;
+      j.ld_f = cv.ld_f; j.ld_dw = cv.ld_dw;
+      if (cv.is_skip && cv.has_bias) {       // a skip conv: its bias gradient may come from the fused wgrad
+        j.dbias = (float*)p->grads[base + cv.slot_bias];
+        j.dbias_src_off = d.dbskip_off;
+      }
       jobs.push_back(j);
       if (cv.train_g) segs.push_back(Seg{j.g, (float*)p->grads[base + cv.slot_g], cv.cout});
     }
@@ -1050,6 +1118,18 @@ int rnvp_plan_bind(rnvp_plan* p, void* const* params, void* const* grads, void* 
     for (auto& e : p->ev_done) RNVP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     RNVP_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   }
+  std::vector<BiasSumJob> biasjobs;
+  for (size_t ci = 0; ci < p->cpl.size(); ++ci) {
+    const CouplingDesc& d = p->cpl[ci];
+    size_t base = ci * p->slots_per_coupling;
+    BiasSumJob bj{};
+    for (const ConvDesc& cv : d.convs)
+      if (cv.is_skip) bj.b[bj.n++] = (const float*)p->params[base + cv.slot_bias];
+    bj.C = d.D; bj.out_off = d.bskip_off;
+    biasjobs.push_back(bj);
+  }
+  if (!p->d_biasjobs) RNVP_CUDA(cudaMalloc(&p->d_biasjobs, biasjobs.size() * sizeof(BiasSumJob)));
+  RNVP_CUDA(cudaMemcpyAsync(p->d_biasjobs, biasjobs.data(), biasjobs.size() * sizeof(BiasSumJob), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   std::vector<BnEvalJob> bnjobs;
   for (size_t ci = 0; ci < p->cpl.size(); ++ci) {
     const CouplingDesc& d = p->cpl[ci];
@@ -1135,7 +1215,7 @@ int rnvp_flow_forward(rnvp_plan* p, const float* x_nchw, float* ll, float* logde
   RNVP_TRY(zero_pass(c, false));
   if (training && p->world > 1) RNVP_TRY(dp_check_equal_batches(&p->dp, batch, c.ws_acc() + 8, c.st));
   RNVP_TRY(clear_padding(c));
-  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size(), 0, (int)p->cpl.size()));
   if (!training) RNVP_TRY(eval_bn_coefs(c));
   if (weight_scale) {
     RNVP_TRY(k_sumsq(p->d_segs, p->nsegs, c.ws_acc(), c.st));
@@ -1258,7 +1338,7 @@ int rnvp_flow_inverse(rnvp_plan* p, const float* z_nchw, float* x_nchw, int batc
   ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
-  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size()));
+  RNVP_TRY(materialize_weights(c, 0, (int)p->h_jobs.size(), 0, (int)p->cpl.size()));
   if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   // factor_out chain (flow_realnvp.py:197-200): in_ckbd[s+1], off[s] = factor_out(in_ckbd[s])
@@ -1311,7 +1391,7 @@ int rnvp_coupling_forward(rnvp_plan* p, int ci, const float* x_nchw, float* y_nc
   ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
-  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size(), ci, 1));
   if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   RNVP_TRY(k_nchw_to_nhwc(x_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));
@@ -1333,7 +1413,7 @@ int rnvp_coupling_inverse(rnvp_plan* p, int ci, const float* y_nchw, float* x_nc
   ++p->fwd_gen;
   RNVP_TRY(zero_pass(c, false));
   RNVP_TRY(clear_padding(c));
-  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size()));
+  RNVP_TRY(materialize_weights(c, d.job0, (int)d.convs.size(), ci, 1));
   if (!training) RNVP_TRY(eval_bn_coefs(c));
   FlowBufs f = flow_bufs(c);
   RNVP_TRY(k_nchw_to_nhwc(y_nchw, f.T[0], batch, d.C, d.S, d.S, c.st));

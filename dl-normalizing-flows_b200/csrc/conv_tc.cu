@@ -78,14 +78,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+      ::"r"(dst), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const void* src, const CUtensorMap* map, int c0, int c1) {
+__device__ __forceinline__ void tma_store_2d(uint32_t src, const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+               ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const void* src, const CUtensorMap* map, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -131,6 +131,26 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Shared-memory accesses through explicit state-space instructions and 32-bit addresses.  The dynamic shared-memory
+// pointer loses its address space in the 1 KB alignment arithmetic, and generic LD.E / ST.E are what the compiler
+// then emits: slower, and -- since a generic store may alias anything -- serialised load -> compute -> store chains.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // 32 lanes x 32 consecutive columns: thread i of the warp gets row (lane base + i), 32 columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -318,7 +338,8 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  const uint32_t smem_a = smem_u32(smem);                            // shared-window address of the ring
+  const uint32_t epi_smem = smem_a + (uint32_t)(STAGES * STAGE_BYTES);
   __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[TC_MAX_STAGES];
   __shared__ __align__(8) uint64_t ready_bar[XF ? TC_MAX_STAGES : 1];   // XF: A tile transformed
@@ -476,11 +497,11 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const float4 sc = *reinterpret_cast<const float4*>(&coef[kc * 32 + 4 * j]);
           const float4 sh = *reinterpret_cast<const float4*>(&coef[XF_MAX_K + kc * 32 + 4 * j]);
           mbar_wait(&full_bar[s], ph);
-          uint8_t* a_tile = smem + s * STAGE_BYTES;
+          const uint32_t a_tile = smem_a + (uint32_t)(s * STAGE_BYTES) + swz_off(r0, j);   // rows r0 + 16 i: + 2048 i
           float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (valid & (1u << i)) v[i] = *reinterpret_cast<const float4*>(a_tile + swz_off(r0 + 16 * i, j));
+            if (valid & (1u << i)) v[i] = lds128(a_tile + 2048u * i);      // (r0 + 16 i) & 7 == r0 & 7: same swizzle
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (valid & (1u << i)) {
@@ -489,12 +510,12 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
               w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
               w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
               w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
-              *reinterpret_cast<float4*>(a_tile + swz_off(r0 + 16 * i, j)) = w;
+              sts128(a_tile + 2048u * i, w);
             }
           }
           fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's reads
           __syncwarp();
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&ready_bar[s])) : "memory");
+          if (lane == 0) mbar_arrive(&ready_bar[s]);
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
@@ -505,8 +526,8 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int ew = warp - 2;                      // epilogue warp index
     const int ci_lo = (ew >> 2) * CH_PER_WARP;    // first column chunk of this warp (two warps share a quarter)
     const int boxes = prm.out_bufs + (prm.has_res ? 1 : 0);
-    uint8_t* res_buf = epi_smem + ew * boxes * EPI_BOX_BYTES;
-    uint8_t* out_buf = res_buf + (prm.has_res ? EPI_BOX_BYTES : 0);   // one or two staging boxes
+    const uint32_t res_buf = epi_smem + (uint32_t)(ew * boxes * EPI_BOX_BYTES);
+    const uint32_t out_buf = res_buf + (prm.has_res ? EPI_BOX_BYTES : 0);   // one or two staging boxes
     float acc_s[CH_PER_WARP], acc_q[CH_PER_WARP]; // per-lane column sums (column c0 + lane), n_tiles == 1
 #pragma unroll
     for (int i = 0; i < CH_PER_WARP; ++i) acc_s[i] = acc_q[i] = 0.f;
@@ -647,7 +668,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (XF || !bnbwd) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
+              float4 r4 = lds128(res_buf + swz_off(lane, j));
               v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
             }
           } else if constexpr (!XF) {
@@ -656,7 +677,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // (sum gm, sum gm*x) into sum gm*xhat = rstd*(sum gm*x - mean*sum gm) in double)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 r4 = *reinterpret_cast<const float4*>(res_buf + swz_off(lane, j));
+              float4 r4 = lds128(res_buf + swz_off(lane, j));
               float4 sc4, sh4;
               const int cbase = nb + 4 * j;
               if (coef_in_smem) {                   // n0 == 0: column index == channel index
@@ -710,7 +731,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int j = 0; j < 32; ++j) v[j] = round_tf32(v[j]);
         }
         // stage the 32x32 result box (swizzled) and hand it to TMA
-        uint8_t* ob = out_buf + (prm.out_bufs == 2 ? (step & 1) * EPI_BOX_BYTES : 0);
+        const uint32_t ob = out_buf + (prm.out_bufs == 2 ? (step & 1) * EPI_BOX_BYTES : 0);
         if (lane == 0) {                                  // the store that last used this buffer has read it
           if (prm.out_bufs == 2) tma_store_wait_read<1>();
           else tma_store_wait_read<0>();
@@ -718,7 +739,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(ob + swz_off(lane, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          sts128(ob + swz_off(lane, j), make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -736,7 +757,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (XF || !bnbwd) {
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              float val = *reinterpret_cast<const float*>(ob + swz_off(r, jc) + wc);
+              float val = lds32(ob + swz_off(r, jc) + wc);
               val = r < rows_valid ? val : 0.f;
               s1 += val;
               s2 = fmaf(val, val, s2);
@@ -747,7 +768,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // read x into registers, so re-reading here would race -- use the register copy instead)
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              float val = *reinterpret_cast<const float*>(ob + swz_off(r, jc) + wc);
+              float val = lds32(ob + swz_off(r, jc) + wc);
               val = r < rows_valid ? val : 0.f;
               s1 += val;
             }
@@ -1239,56 +1260,67 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
         const int c16 = e & 7, er0 = e >> 3;
         const int lch = 8 * ((c16 >> 1) ^ (er0 & 3)) + 4 * (c16 & 1);     // logical channel (within a box) of this chunk
         const int Smask = prm.S - 1;
-        int as = 0;
-        uint32_t aph = 0;
+        const uint32_t a_ring_a = smem_u32(a_ring), b_ring_a = smem_u32(b_ring);
+        const uint32_t my_off = (uint32_t)(er0 * 128 + c16 * 16);         // this thread's chunk in rows er0 + 16 i (+ 2048 i)
+        int as = 0, bs = 0;
+        uint32_t aph = 0, bph = 0;
         for (int t = t_begin; t < t_end; ++t) {
           if (do_bias) {
-            const int bi = t - t_begin, bs = bi % WG_B_STAGES;
-            mbar_wait(&b_full[bs], (bi / WG_B_STAGES) & 1);
+            mbar_wait(&b_full[bs], bph);
             if (q < nbx) {
-              const float* box = reinterpret_cast<const float*>(b_ring + bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES);
-#pragma unroll 16
-              for (int r = 0; r < 64; ++r) part[r & 3] += box[r * 32 + lane];
+              const uint32_t box = b_ring_a + (uint32_t)(bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES) + 4u * lane;
+#pragma unroll
+              for (int r0 = 0; r0 < 64; r0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = lds32(box + 128u * (r0 + r));
+#pragma unroll
+                for (int r = 0; r < 16; ++r) part[r & 3] += v[r];
+              }
             }
             __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&b_empty[bs])) : "memory");
+            if (lane == 0) mbar_arrive(&b_empty[bs]);
+            if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1; }
           }
           if (xf) {
             for (int mg = 0; mg < groups; ++mg) {
               const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);
               mbar_wait(&a_full[as], aph);
+              const uint32_t stage = a_ring_a + (uint32_t)(as * WG_A_STAGE_BYTES) + my_off;
               for (int tli = 0; tli < tl_n; ++tli) {
                 const int tap = tap0 + mg * prm.tpm + tli;
                 int dy = 0, dx = 0;
                 if (prm.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
-                uint32_t valid = 0;
+                bool valid[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   const int p = t * 64 + er0 + 16 * i;
                   const int x = (p & Smask) + dx, y = ((p >> prm.log2S) & Smask) + dy;
-                  if (p < prm.P && (unsigned)x < (unsigned)prm.S && (unsigned)y < (unsigned)prm.S) valid |= 1u << i;
+                  valid[i] = p < prm.P && (unsigned)x < (unsigned)prm.S && (unsigned)y < (unsigned)prm.S;
                 }
                 for (int j = 0; j < kb; ++j) {
-                  uint8_t* box = a_ring + as * WG_A_STAGE_BYTES + (tli * kb + j) * WG_BOX_BYTES;
+                  const uint32_t box = stage + (uint32_t)((tli * kb + j) * WG_BOX_BYTES);
                   const float4 sc = *reinterpret_cast<const float4*>(&wcoef[0][32 * j + lch]);
                   const float4 sh = *reinterpret_cast<const float4*>(&wcoef[1][32 * j + lch]);
+                  float4 w[4];
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    if (valid[i]) w[i] = lds128(box + 2048u * i);
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
-                    if (valid & (1u << i)) {
-                      float4* ptr = reinterpret_cast<float4*>(box + (er0 + 16 * i) * 128 + c16 * 16);
-                      float4 w = *ptr;
-                      w.x = round_tf32(fmaxf(fmaf(w.x, sc.x, sh.x), 0.f));
-                      w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
-                      w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
-                      w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
-                      *ptr = w;
+                    if (valid[i]) {
+                      w[i].x = round_tf32(fmaxf(fmaf(w[i].x, sc.x, sh.x), 0.f));
+                      w[i].y = round_tf32(fmaxf(fmaf(w[i].y, sc.y, sh.y), 0.f));
+                      w[i].z = round_tf32(fmaxf(fmaf(w[i].z, sc.z, sh.z), 0.f));
+                      w[i].w = round_tf32(fmaxf(fmaf(w[i].w, sc.w, sh.w), 0.f));
+                      sts128(box + 2048u * i, w[i]);
                     }
                   }
                 }
               }
               fence_proxy_async();
               __syncwarp();
-              if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&a_ready[as])) : "memory");
+              if (lane == 0) mbar_arrive(&a_ready[as]);
               if (++as == WG_A_STAGES) { as = 0; aph ^= 1; }
             }
           }

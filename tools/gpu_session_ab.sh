@@ -25,6 +25,9 @@ for s in "$@"; do
       env $envs timeout 600 python tools/bench_coupling.py > $OUT/${TAG}_cpl_${name}.log 2>&1 ;;
     benchenv:*) name=$(echo $s | cut -d: -f2); envs=$(echo $s | cut -d: -f3 | tr ',' ' ')
       env $envs timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-prof > $OUT/${TAG}_bench_${name}.json 2> $OUT/${TAG}_bench_${name}.err ;;
+    targetsenv:*) name=$(echo $s | cut -d: -f2); envs=$(echo $s | cut -d: -f3 | tr ',' ' ')
+      env $envs TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets_${name}.log 2>&1 ;;
+    hosttime) timeout 300 python tools/host_time.py > $OUT/${TAG}_hosttime.log 2>&1; B=64 timeout 300 python tools/host_time.py >> $OUT/${TAG}_hosttime.log 2>&1 ;;
     targets) TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets.log 2>&1 ;;
     ncu_targets) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_(fwd|wgrad)_tf32" -c 27 \
                    -o $OUT/${TAG}_targets python tools/ncu_targets.py > $OUT/${TAG}_ncu_targets.log 2>&1 ;;

@@ -71,6 +71,18 @@ def wgrad_bn(d, i):
                                  d["k"], d["D"], ptr(d["save"]), d["D"], st))
 
 
+def wgrad_bias(d, i):
+    j = i % d["nset"]
+    check(lib.rnvp_conv_wgrad(ptr(d["x"][j]), ptr(d["r"][j]), ptr(d["dw"]), ptr(d["db"]), B, d["S"], d["D"], d["D"], d["D"], d["k"],
+                              d["D"], 1, st))
+
+
+def wgrad_bn_nob(d, i):
+    j = i % d["nset"]
+    check(lib.rnvp_conv_wgrad_bn(ptr(d["x"][j]), ptr(d["r"][j]), ptr(d["dw"]), None, B, d["S"], d["D"], d["D"], d["D"],
+                                 d["k"], d["D"], ptr(d["save"]), d["D"], st))
+
+
 def dgrad_bn(d, i):
     j = i % d["nset"]
     check(lib.rnvp_conv_dgrad_bn(ptr(d["r"][j]), ptr(d["w"]), ptr(d["x"][j]), ptr(d["save"]), ptr(d["y"][j]), ptr(d["sums2"]),
@@ -82,6 +94,12 @@ s32k3 = make(32, 64, 3)
 CASES = [("fwd_bn S64 1x1", fwd_bn, s64), ("fwd_bn S32 1x1", fwd_bn, s32), ("wgrad S64 1x1", wgrad, s64),
          ("wgrad S32 1x1", wgrad, s32), ("wgrad_bn S64 1x1", wgrad_bn, s64), ("wgrad_bn S32 1x1", wgrad_bn, s32),
          ("dgrad_bn S32 1x1", dgrad_bn, s32), ("fwd S32 3x3", fwd, s32k3), ("wgrad S32 3x3", wgrad, s32k3)]
+if TIME:
+    s16 = make(16, 128, 1)
+    CASES += [("wgrad+bias S64 1x1", wgrad_bias, s64), ("wgrad_bn-nobias S64", wgrad_bn_nob, s64),
+              ("wgrad+bias S32 1x1", wgrad_bias, s32), ("wgrad_bn-nobias S32", wgrad_bn_nob, s32),
+              ("wgrad S16 1x1", wgrad, s16), ("wgrad_bn S16 1x1", wgrad_bn, s16), ("wgrad_bn-nobias S16", wgrad_bn_nob, s16),
+              ("fwd_bn S16 1x1", fwd_bn, s16), ("dgrad_bn S16 1x1", dgrad_bn, s16)]
 torch.cuda.synchronize()
 for name, fn, d in CASES:
     if TIME:

@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling: the WHOLE job's batch, split evenly over the GPUs (BASELINE configs[3]: 4096 "
                          "samples, configs[4]: global batch 2048); overrides --batch")
-    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--math", default="tf32", choices=["tf32", "fp32", "tf32x3"],
+                    help="tf32: tcgen05 TF32 (default, the benchmarked tier); tf32x3: 3xTF32 split operands on the tensor cores "
+                         "(fp32-accurate); fp32: CUDA-core fp32")
     ap.add_argument("--mode", default="train", choices=["train", "sample"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prof", action="store_true")
@@ -290,12 +292,13 @@ def conv_alg_bytes_and_flops(kind, S, taps, cin, cout, B, fused_reduce=True):
 def kernel_name_of(kind, taps, cin, cout, math, xform):
     """The CUDA kernel (as ncu names it) a profiled launch class runs in."""
     if kind in (0, 1):
-        if math != "tf32":
+        if math == "fp32":
             return "conv_fwd_fp32_kernel"
         bn = 32 if cout <= 32 else (64 if cout <= 64 else 128)
-        return f"conv_fwd_tf32_kernel<{bn},{1 if (kind == 0 and xform) else 0}>"
+        x3 = 1 if math == "tf32x3" else 0            # <BN, transform warps, coupling epilogue, 3xTF32>
+        return f"conv_fwd_tf32_kernel<{bn},{1 if (x3 or (kind == 0 and xform)) else 0},0,{x3}>"
     if kind == 2:
-        return "conv_wgrad_tf32_kernel" if math == "tf32" else "conv_wgrad_fp32_kernel"
+        return "conv_wgrad_tf32_kernel" if math != "fp32" else "conv_wgrad_fp32_kernel"
     return "bn_relu_kernel" if kind == 3 else "bn_bwd_apply_kernel"
 
 
@@ -345,6 +348,11 @@ def dp_consistency_check(pkg, model, net, dev, rank, world):
     g = torch.Generator().manual_seed(77)
     xs = torch.randn(world * b, CFG["channels"], CFG["image"], CFG["image"], generator=g).to(dev)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    # The check runs in the fp32 tier: at a global batch of 8 the TF32 gradient of this 28-coupling train-mode stack is
+    # chaotic (two valid summation orders differ by O(0.1)), which would make the comparison a coin toss;
+    # the data-parallel plumbing under test (shards, statistic exchange, gradient all-reduce) is the same in every tier.
+    math_was = "tf32" if net.engine().math == pkg.rnvp_cabi.MATH_TF32 else ("fp32" if net.engine().math == pkg.rnvp_cabi.MATH_FP32 else "tf32x3")
+    net.set_math("fp32")
     net.train()
     net.zero_grad(set_to_none=True)
     ll, ws = model(xs[rank * b:(rank + 1) * b].contiguous())
@@ -360,7 +368,7 @@ def dp_consistency_check(pkg, model, net, dev, rank, world):
                           pkg.Hyperparameters(CFG["base_dim"], CFG["res_blocks"], True, True, True, True),
                           **({} if CFG["num_scales"] == 5 else {"num_scales": CFG["num_scales"]})).to(dev)
         ref.load_state_dict(sd)
-        ref.set_math("tf32" if net.engine().math == pkg.rnvp_cabi.MATH_TF32 else "fp32")
+        ref.set_math("fp32")
         ref.train()
         ll1, ws1 = ref(xs)
         (-ll1.mean() + 5e-5 * ws1).backward()
@@ -368,8 +376,10 @@ def dp_consistency_check(pkg, model, net, dev, rank, world):
         e_ll = float((torch.cat(gathered) - ll1.detach()).abs().max() / ll1.detach().abs().max())
         e_g = float((gdp - g1).norm() / g1.norm())
         detail = {"ll_rel": e_ll, "grad_rel_l2": e_g, "global_batch": world * b}
-        ok = e_ll < 1e-4 and e_g < 0.1
+        detail["math"] = "fp32"
+        ok = e_ll < 1e-4 and e_g < 2e-2
         del ref
+    net.set_math(math_was)
     net.load_state_dict(sd)                        # running statistics back to where they were
     net.zero_grad(set_to_none=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
@@ -553,7 +563,7 @@ def run_b200(args):
                 json.dump({"batch": B, "profiled_steps": nprof, "classes": classes}, f, indent=0)
         for r in classes:
             by_kind[names[r["kind"]]] = by_kind.get(names[r["kind"]], 0.0) + r["ms"] / nprof
-        xform_on = args.math == "tf32" and os.environ.get("RNVP_XFORM", "1") != "0"
+        xform_on = args.math != "fp32" and os.environ.get("RNVP_XFORM", "1") != "0"
         groups = {}
         for r in classes:
             byt, fl = conv_alg_bytes_and_flops(r["kind"], r["S"], r["taps"], r["cin"], r["cout"], B,

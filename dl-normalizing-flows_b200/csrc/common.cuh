@@ -141,6 +141,10 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 __device__ __forceinline__ float maybe_round(float x, int on) { return on ? round_tf32(x) : x; }
+// what tcgen05 kind::tf32 reads from an fp32 word; x - trunc_tf32(x) is exact in fp32 (the "lo" operand of the
+// 3xTF32 tier)
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 
 // ---------------------------------------------------------------------------------------------------------
 // One-shot all-reduce of a small double vector over NVLink peer memory, folded INTO the kernel that consumes the

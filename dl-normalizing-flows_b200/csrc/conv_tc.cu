@@ -327,15 +327,30 @@ __device__ __forceinline__ void xf_coefficients(const ConvTcParams& prm, float* 
   }
 }
 
-template <int BN, int XF, int CPL>
+// X3 = 1 ("3xTF32", the fp32-accurate tensor-core tier; needs XF = 1 for its transform warps): every operand is split
+// into hi = its TF32 truncation (what the tensor core reads from an fp32 word anyway, so hi needs no store) and
+// lo = x - hi (exact in fp32, <= 13 significant bits), and each K step issues three MMAs, lo*hi + hi*lo + hi*hi, into
+// the same fp32 accumulator.  The operand error left is ~2^-21 relative (lo*lo dropped, lo itself truncated to TF32);
+// what bounds the tier in practice is the tensor core's fp32 ACCUMULATION, which truncates (measured: rounding hi and lo
+// to nearest instead changed neither the per-op error, 1.0e-5 vs 1.1e-5 of max at K = 1440, nor the log-likelihood
+// errors, and cost 23 % of the step).  A stage holds [A hi | B hi | A lo | B lo]: A lo is written by the transform
+// warps (after the BN prologue, if any -- nothing is rounded in this tier), B lo arrives by TMA from the lo copy of
+// the weights that the weight-norm kernel writes next to them (tmBlo).
+template <int BN, int XF, int CPL, int X3>
 __global__ void __launch_bounds__(TcCfg<BN, XF>::THREADS, TcCfg<BN, XF>::MIN_CTAS)
 conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmR,
-                     const ConvTcParams prm) {
+                     const __grid_constant__ CUtensorMap tmBlo, const ConvTcParams prm) {
+  static_assert(!X3 || XF, "the 3xTF32 split needs the transform warps");
   const int STAGES = prm.stages;
   constexpr int B_TILE_BYTES = BN * 128;
-  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int HALF_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  constexpr int STAGE_BYTES = X3 ? 2 * HALF_BYTES : HALF_BYTES;
+  // 3xTF32 keeps the two small products (lo*hi, hi*lo) in their own accumulator next to the main one: the tensor core
+  // truncates after every accumulation step, and this way the main accumulator takes 4 such steps per chunk instead
+  // of 12 (the lo accumulator's truncation is relative to values 2^-11 times smaller); the epilogue adds the two.
+  constexpr int ACC_COLS = X3 ? 2 * BN : BN;              // columns of one accumulator buffer: [main | lo]
+  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_a = smem_u32(smem);                            // shared-window address of the ring
@@ -365,6 +380,7 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     if (prm.has_res) prefetch_tmap(&tmR);
+    if (X3) prefetch_tmap(&tmBlo);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -418,9 +434,10 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int kk = 0; kk < prm.kps; ++kk, ++kc) {
               mbar_wait(&empty_bar[s], ph);
               uint8_t* a_dst = smem + s * STAGE_BYTES;
-              mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+              mbar_expect_tx(&full_bar[s], HALF_BYTES + (X3 ? B_TILE_BYTES : 0));
               tma_load_5d(a_dst, &tmA, &full_bar[s], kk * 32, col0 + dx, row0 + dy, img0, seg);
               tma_load_3d(a_dst + A_TILE_BYTES, &tmB, &full_bar[s], kc * 32, n0, tap);
+              if (X3) tma_load_3d(a_dst + HALF_BYTES + A_TILE_BYTES, &tmBlo, &full_bar[s], kc * 32, n0, tap);
               if (++s == STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -445,16 +462,26 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int as = ti & 1;
       mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
       for (int it = 0; it < iters; ++it) {
         mbar_wait(XF ? &ready_bar[XF ? s : 0] : &full_bar[s], phase);   // XF: wait for the transformed tile
         tc_fence_after();
         const uint64_t ad = a_desc0 + soff, bd = b_desc0 + soff;
         if (leader) {
-          umma_tf32(d_tmem, ad, bd, idesc, it != 0);          // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
-          umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1);
-          umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1);
-          umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1);
+          if constexpr (X3) {
+            constexpr uint64_t LO = (uint64_t)(HALF_BYTES >> 4);   // address-field distance of the lo tiles
+#pragma unroll
+            for (int k = 0; k < 8; k += 2) {
+              umma_tf32(d_tmem + BN, ad + LO + k, bd + k, idesc, (it != 0) | (k != 0));     // lo accumulator
+              umma_tf32(d_tmem + BN, ad + k, bd + LO + k, idesc, 1);
+              umma_tf32(d_tmem, ad + k, bd + k, idesc, (it != 0) | (k != 0));               // main accumulator
+            }
+          } else {
+            umma_tf32(d_tmem, ad, bd, idesc, it != 0);        // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
+            umma_tf32(d_tmem, ad + 2, bd + 2, idesc, 1);
+            umma_tf32(d_tmem, ad + 4, bd + 4, idesc, 1);
+            umma_tf32(d_tmem, ad + 6, bd + 6, idesc, 1);
+          }
           umma_commit(&empty_bar[s]);                         // frees the smem stage when these MMAs retire
         }
         __syncwarp();
@@ -473,8 +500,9 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int j = t & 7, r0 = t >> 3;
     const int Smask = prm.S - 1;
     // the BN coefficients are only needed here: compute them while the producer's first loads are in flight
+    const bool xf_bn = prm.xf_mode != 3;          // mode 3 (3xTF32 tier): no batch norm in front of this conv, split only
     if constexpr (XF) {
-      xf_coefficients(prm, coef, coef + XF_MAX_K, prm.kchunks * 32, blockIdx.x == 0, t, 32 * TcCfg<BN, XF>::XF_WARPS);
+      if (xf_bn) xf_coefficients(prm, coef, coef + XF_MAX_K, prm.kchunks * 32, blockIdx.x == 0, t, 32 * TcCfg<BN, XF>::XF_WARPS);
       asm volatile("bar.sync 2, %0;" ::"n"(32 * TcCfg<BN, XF>::XF_WARPS) : "memory");
     }
     int s = 0;
@@ -494,23 +522,43 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if (p < prm.P && (unsigned)x < (unsigned)prm.S && (unsigned)y < (unsigned)prm.S) valid |= 1u << i;
         }
         for (int kc = 0; kc < prm.kchunks; ++kc) {
-          const float4 sc = *reinterpret_cast<const float4*>(&coef[kc * 32 + 4 * j]);
-          const float4 sh = *reinterpret_cast<const float4*>(&coef[XF_MAX_K + kc * 32 + 4 * j]);
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (xf_bn) {
+            sc = *reinterpret_cast<const float4*>(&coef[kc * 32 + 4 * j]);
+            sh = *reinterpret_cast<const float4*>(&coef[XF_MAX_K + kc * 32 + 4 * j]);
+          }
           mbar_wait(&full_bar[s], ph);
           const uint32_t a_tile = smem_a + (uint32_t)(s * STAGE_BYTES) + swz_off(r0, j);   // rows r0 + 16 i: + 2048 i
           float4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (valid & (1u << i)) v[i] = lds128(a_tile + 2048u * i);      // (r0 + 16 i) & 7 == r0 & 7: same swizzle
+          if constexpr (X3) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (valid & (1u << i)) {
-              float4 w = v[i];
-              w.x = round_tf32(fmaxf(fmaf(w.x, sc.x, sh.x), 0.f));
-              w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
-              w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
-              w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
-              sts128(a_tile + 2048u * i, w);
+            for (int i = 0; i < 8; ++i) {
+              float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);          // zero-filled (out-of-image) rows: lo = 0 as well
+              if (valid & (1u << i)) {
+                float4 w = v[i];
+                if (xf_bn) {
+                  w.x = fmaxf(fmaf(w.x, sc.x, sh.x), 0.f); w.y = fmaxf(fmaf(w.y, sc.y, sh.y), 0.f);
+                  w.z = fmaxf(fmaf(w.z, sc.z, sh.z), 0.f); w.w = fmaxf(fmaf(w.w, sc.w, sh.w), 0.f);
+                }
+                lo = make_float4(w.x - trunc_tf32(w.x), w.y - trunc_tf32(w.y), w.z - trunc_tf32(w.z), w.w - trunc_tf32(w.w));
+                if (xf_bn) sts128(a_tile + 2048u * i, w);            // hi = the value itself: the tensor core truncates it
+              }
+              sts128(a_tile + (uint32_t)HALF_BYTES + 2048u * i, lo);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (valid & (1u << i)) {
+                float4 w = v[i];
+                w.x = round_tf32(fmaxf(fmaf(w.x, sc.x, sh.x), 0.f));
+                w.y = round_tf32(fmaxf(fmaf(w.y, sc.y, sh.y), 0.f));
+                w.z = round_tf32(fmaxf(fmaf(w.z, sc.z, sh.z), 0.f));
+                w.w = round_tf32(fmaxf(fmaf(w.w, sc.w, sh.w), 0.f));
+                sts128(a_tile + 2048u * i, w);
+              }
             }
           }
           fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core's reads
@@ -580,9 +628,16 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float ssum = 0.f;
         for (int cb = c_lo; cb < c_hi; cb += 8) {
           float tv[8], lv[8];
-          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS);
           tmem_ld_32x8(tb + (uint32_t)cb, tv);
           tmem_ld_32x8(tb + (uint32_t)(g.cio + cb), lv);
+          if constexpr (X3) {
+            float t2[8], l2[8];
+            tmem_ld_32x8(tb + (uint32_t)(BN + cb), t2);
+            tmem_ld_32x8(tb + (uint32_t)(BN + g.cio + cb), l2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { tv[j] += t2[j]; lv[j] += l2[j]; }
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int c = cb + j;
@@ -648,7 +703,16 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int nb = n0 + c0;
         if (!store_st || ci >= chunks_per_tile || nb >= prm.n) break;
         float v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + c0), v);
+        if constexpr (X3) {
+#pragma unroll
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float v2[8];
+            tmem_ld_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + BN + c0 + j8), v2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j8 + j] += v2[j];
+          }
+        }
         if (prm.bias) {
           if (nb + 32 <= prm.n) {
 #pragma unroll
@@ -912,7 +976,7 @@ struct FwdKernelInfo {
   int max_stages = 0, by_regs = 0, static_smem = 0;
   int status = RNVP_OK;
 };
-template <int BN, int XF, int CPL>
+template <int BN, int XF, int CPL, int X3>
 static const FwdKernelInfo& fwd_kernel_info() {
   static const FwdKernelInfo info = [] {
     FwdKernelInfo k;
@@ -921,12 +985,12 @@ static const FwdKernelInfo& fwd_kernel_info() {
                           : (BN == 128 ? "RNVP_TC_STAGES_128" : (BN == 64 ? "RNVP_TC_STAGES_64" : "RNVP_TC_STAGES_32"));
     k.max_stages = env_int(name, 1, TC_MAX_STAGES, TcCfg<BN, XF>::STAGES);
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN, XF, CPL>) != cudaSuccess) { k.status = RNVP_ERR_CUDA; return k; }
+    if (cudaFuncGetAttributes(&fa, conv_fwd_tf32_kernel<BN, XF, CPL, X3>) != cudaSuccess) { k.status = RNVP_ERR_CUDA; return k; }
     k.by_regs = 65536 / (pad_to(fa.numRegs * 32, 256) * (THREADS / 32));
     k.static_smem = (int)fa.sharedSizeBytes;
-    if (cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              227 * 1024 - k.static_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaFuncSetAttribute(conv_fwd_tf32_kernel<BN, XF, CPL, X3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared) != cudaSuccess)
       k.status = RNVP_ERR_CUDA;
     return k;
@@ -934,9 +998,9 @@ static const FwdKernelInfo& fwd_kernel_info() {
   return info;
 }
 
-template <int BN, int XF, int CPL = 0>
+template <int BN, int XF, int CPL = 0, int X3 = 0>
 static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
-  CUtensorMap tmA, tmB, tmY, tmR;
+  CUtensorMap tmA, tmB, tmY, tmR, tmBlo;
   int bw = 0, bh = 0, bn = 0;
   pixel_box(a.S, 128, &bw, &bh, &bn);
   RNVP_TRY(make_act_map(&tmA, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B, a.segs, a.seg_stride));
@@ -945,30 +1009,36 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   cuuint64_t strides[2] = {(cuuint64_t)ldw * 4, (cuuint64_t)a.npad * ldw * 4};
   cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
   RNVP_TRY(encode_map(&tmB, a.w, 3, dims, strides, box));
+  if (X3) RNVP_TRY(encode_map(&tmBlo, a.w + a.w_lo_delta, 3, dims, strides, box));
+  else tmBlo = tmB;
   const float* rsrc = a.bn_x ? a.bn_x : a.res;
   RNVP_TRY(make_row_map(&tmY, a.y, prm.P, a.n, a.ldy));
   if (rsrc) RNVP_TRY(make_row_map(&tmR, rsrc, prm.P, a.n, a.ldy));
   else tmR = tmY;
   constexpr int THREADS = TcCfg<BN, XF>::THREADS;
-  const FwdKernelInfo& ki = fwd_kernel_info<BN, XF, CPL>();
+  const FwdKernelInfo& ki = fwd_kernel_info<BN, XF, CPL, X3>();
   RNVP_REQUIRE(ki.status == RNVP_OK, "conv: cudaFuncGetAttributes / cudaFuncSetAttribute failed");
   // shared-memory plan: epilogue staging (a residual box only when the layer has one; one output box per warp
   // for the 32-wide tile, whose warps stage one box per tile) + as many ring stages as keep MIN_CTAS resident
-  prm.out_bufs = env_int("RNVP_TC_OUTBUFS", 1, 2, BN == 32 ? 1 : 2);
+  prm.out_bufs = env_int("RNVP_TC_OUTBUFS", 1, 2, (BN == 32 || X3) ? 1 : 2);
   const int EPI = TcCfg<BN, XF>::EPI_WARPS * (prm.out_bufs + (prm.has_res ? 1 : 0)) * EPI_BOX_BYTES;
-  const int budget = (228 * 1024) / TcCfg<BN, XF>::MIN_CTAS - 1024 /* driver */ - ki.static_smem - 1024 /* alignment */;
-  int stages = (budget - EPI) / (A_TILE_BYTES + BN * 128);
+  const int stage_bytes = (X3 ? 2 : 1) * (A_TILE_BYTES + BN * 128);          // 3xTF32: hi and lo tiles
+  int budget = (228 * 1024) / TcCfg<BN, XF>::MIN_CTAS - 1024 /* driver */ - ki.static_smem - 1024 /* alignment */;
+  if ((budget - EPI) / stage_bytes < 2)                                       // the doubled stages want the whole SM
+    budget = 228 * 1024 - 1024 - ki.static_smem - 1024;
+  int stages = (budget - EPI) / stage_bytes;
   if (stages > ki.max_stages) stages = ki.max_stages;
   if (stages < 2) stages = 2;
   prm.stages = stages;
-  const int smem = stages * (A_TILE_BYTES + BN * 128) + EPI + 1024;
+  const int smem = stages * stage_bytes + EPI + 1024;
   RNVP_REQUIRE(smem + ki.static_smem <= 227 * 1024, "conv: shared-memory plan of %d bytes does not fit", smem);
   // resident CTAs per SM from the kernel's own footprint: shared memory (dynamic + static + 1 KB the driver
   // reserves per CTA) against the 228 KB of an SM, registers against the 64 K file, TMEM columns
   // (cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports this kernel: it answered 1 where 2 fit)
   int ctas = (228 * 1024) / (smem + ki.static_smem + 1024);
   if (ctas > ki.by_regs) ctas = ki.by_regs;
-  if (ctas > 512 / (2 * BN < 32 ? 32 : 2 * BN)) ctas = 512 / (2 * BN < 32 ? 32 : 2 * BN);
+  constexpr int tmem_cols = (X3 ? 4 : 2) * BN < 32 ? 32 : (X3 ? 4 : 2) * BN;
+  if (ctas > 512 / tmem_cols) ctas = 512 / tmem_cols;
   if (ctas < 1) ctas = 1;
   ctas = env_int("RNVP_TC_CTAS", 1, 8, ctas);
   if (getenv("RNVP_DEBUG")) {
@@ -985,7 +1055,7 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   int tiles = prm.m_tiles * prm.n_tiles;
   int grid = kNumSMs * ctas;
   if (grid > tiles) grid = tiles;
-  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN, XF, CPL>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, prm));
+  RNVP_CUDA(launch_pdl(conv_fwd_tf32_kernel<BN, XF, CPL, X3>, dim3(grid), dim3(THREADS), (size_t)smem, st, tmA, tmB, tmY, tmR, tmBlo, prm));
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }
@@ -1026,6 +1096,31 @@ int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st) {
   prm.log2S = 0;
   while ((1 << prm.log2S) < a.S) ++prm.log2S;
   prm.rev = next_sweep_dir();
+  if (a.x3) {
+    // fp32-accurate tier: 3xTF32.  Every conv runs the transform-warp kernel (the BN prologue, or a plain split).
+    RNVP_REQUIRE(a.bn_x == nullptr && a.round_out == 0 && a.w_lo_delta != 0,
+                 "3xTF32: no fused BN-backward epilogue, no operand rounding, and the lo copy of the weights is needed");
+    RNVP_REQUIRE(a.segs * a.kpad <= XF_MAX_K || a.xf == nullptr, "3xTF32 BN prologue: too many input channels");
+    prm.xf_mode = 3;
+    if (a.xf) {
+      const BnPrologue& x = *a.xf;
+      RNVP_REQUIRE(x.mode == 2 ? x.save != nullptr : (x.gamma && x.beta && x.run_mean && x.run_var), "BN prologue: missing coefficient source");
+      RNVP_REQUIRE(x.mode != 1 || (x.sums && x.save), "BN prologue: training mode needs sums and save");
+      prm.xf_mode = x.mode; prm.xf_C = x.C; prm.xf_sums = x.sums; prm.xf_count = x.count;
+      prm.xf_gamma = x.gamma; prm.xf_beta = x.beta; prm.xf_rm = x.run_mean; prm.xf_rv = x.run_var; prm.xf_save = x.save;
+      prm.xf_xg = x.xg;
+    }
+    if (a.cpl && a.cpl->mode) {
+      RNVP_REQUIRE(a.xf && a.n <= 128 && a.bias && !a.res && a.n == 2 * a.cpl->g.cio, "coupling epilogue: bad out conv");
+      prm.cpl = *a.cpl;
+      if (a.n <= 32) return launch_fwd<32, 1, 1, 1>(a, prm, st);
+      if (a.n <= 64) return launch_fwd<64, 1, 1, 1>(a, prm, st);
+      return launch_fwd<128, 1, 1, 1>(a, prm, st);
+    }
+    if (a.n <= 32) return launch_fwd<32, 1, 0, 1>(a, prm, st);
+    if (a.n <= 64) return launch_fwd<64, 1, 0, 1>(a, prm, st);
+    return launch_fwd<128, 1, 0, 1>(a, prm, st);
+  }
   if (a.xf) {
     const BnPrologue& x = *a.xf;
     RNVP_REQUIRE(a.bn_x == nullptr, "BN prologue and BN-backward epilogue are separate kernels");
@@ -1092,6 +1187,10 @@ struct WgradTcParams {
   // main loop) rewrite every landed x box to tf32(relu(x * scale + shift)) with the coefficients the forward saved
   const float* xf_save;                     // [4C] mean, rstd, scale, shift, or null
   int xf_C, log2S;
+  // 3xTF32 (fp32-accurate tier): the epilogue warps split every landed x and dy box into hi (in place: the tensor
+  // core truncates the fp32 word itself) and lo = v - trunc(v), written a_half / b_half bytes further into the stage;
+  // three MMAs per K step (lo*hi, hi*lo, hi*hi)
+  int x3, a_half, b_half;
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
@@ -1113,13 +1212,15 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
   uint8_t* b_ring = smem + prm.ring_bytes - WG_B_STAGES * WG_B_STAGE_BYTES;
   __shared__ __align__(8) uint64_t a_full[WG_MAX_STAGES], a_empty[WG_MAX_STAGES];
   __shared__ __align__(8) uint64_t b_full[WG_MAX_STAGES], b_empty[WG_MAX_STAGES];
-  __shared__ __align__(8) uint64_t a_ready[WG_MAX_STAGES];            // BN prologue: x boxes of the stage transformed
+  __shared__ __align__(8) uint64_t a_ready[WG_MAX_STAGES];            // BN prologue / 3xTF32: x boxes of the stage transformed
+  __shared__ __align__(8) uint64_t b_ready[WG_MAX_STAGES];            // 3xTF32: dy boxes of the stage split
   __shared__ __align__(8) uint64_t acc_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float wcoef[2][128];                       // (scale | shift) of this CTA's k-tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool xf = prm.xf_save != nullptr;
+  const bool x3 = prm.x3 != 0;
   int bx = blockIdx.x;
   const int kt = bx % prm.k_tiles; bx /= prm.k_tiles;
   const int nt = bx % prm.n_tiles; bx /= prm.n_tiles;
@@ -1141,7 +1242,12 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
     for (int s = 0; s < WG_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_ready[s], 4); }
     // a dy stage is released by the MMA commit and, when this CTA owns the bias gradient, by the four
     // epilogue warps that read the boxes for the column sums
-    for (int s = 0; s < WG_B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], do_bias ? 5 : 1); }
+    // (3xTF32: the warps hand the stage to the MMA warp through b_ready instead and never touch it afterwards)
+    for (int s = 0; s < WG_B_STAGES; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], (do_bias && !x3) ? 5 : 1);
+      mbar_init(&b_ready[s], 4);
+    }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
   }
@@ -1212,20 +1318,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
         uint32_t aph = 0, bph = 0;
         uint64_t aoff = 0, boff = 0;
         for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(&b_full[bs], bph);
+          mbar_wait(x3 ? &b_ready[bs] : &b_full[bs], bph);
           tc_fence_after();
           const uint64_t bd = b_desc0 + boff;
           const uint32_t acc = (t != t_begin);
+          const uint64_t alo = (uint64_t)(prm.a_half >> 4), blo = (uint64_t)(prm.b_half >> 4);
           for (int mg = 0; mg < groups; ++mg) {
-            mbar_wait(xf ? &a_ready[as] : &a_full[as], aph);
+            mbar_wait((xf || x3) ? &a_ready[as] : &a_full[as], aph);
             tc_fence_after();
             const uint64_t ad = a_desc0 + aoff;
             const uint32_t d = tmem_base + (uint32_t)(mg * N);
             if (leader) {
               // 8 x (K = 8 pixels = two 512-byte swizzle atoms = 1024 bytes -> +64 in the address field)
-              umma_tf32(d, ad, bd, idesc, acc);
+              if (x3) {
 #pragma unroll
-              for (int ks = 1; ks < 8; ++ks) umma_tf32(d, ad + 64 * ks, bd + 64 * ks, idesc, 1);
+                for (int ks = 0; ks < 8; ++ks) {
+                  umma_tf32(d, ad + alo + 64 * ks, bd + 64 * ks, idesc, acc | (uint32_t)(ks != 0));
+                  umma_tf32(d, ad + 64 * ks, bd + blo + 64 * ks, idesc, 1);
+                  umma_tf32(d, ad + 64 * ks, bd + 64 * ks, idesc, 1);
+                }
+              } else {
+                umma_tf32(d, ad, bd, idesc, acc);
+#pragma unroll
+                for (int ks = 1; ks < 8; ++ks) umma_tf32(d, ad + 64 * ks, bd + 64 * ks, idesc, 1);
+              }
               umma_commit(&a_empty[as]);
             }
             __syncwarp();
@@ -1246,7 +1362,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
       const int m = q * 32 + lane;               // accumulator row = (tap_local, k)
       const int kc = kb * 32;
       const int tl = m / kc, k = m % kc;
-      if (do_bias || xf) {
+      if (do_bias || xf || x3) {
         // Main-loop duties of the otherwise idle epilogue warps, tile by tile in the producer's order:
         //  (a) dbias[n] = sum_p dy[p,n]: warp q owns dy box q (32 channels x 64 pixel rows of 128 bytes).  Within a
         //      row the four 32-byte chunks are XOR-permuted by (row & 3) ("128B swizzle, 32B atom" = Swizzle<2,5,2>),
@@ -1265,9 +1381,9 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
         int as = 0, bs = 0;
         uint32_t aph = 0, bph = 0;
         for (int t = t_begin; t < t_end; ++t) {
-          if (do_bias) {
+          if (do_bias || x3) {
             mbar_wait(&b_full[bs], bph);
-            if (q < nbx) {
+            if (do_bias && q < nbx) {
               const uint32_t box = b_ring_a + (uint32_t)(bs * WG_B_STAGE_BYTES + q * WG_BOX_BYTES) + 4u * lane;
 #pragma unroll
               for (int r0 = 0; r0 < 64; r0 += 16) {
@@ -1278,11 +1394,30 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
                 for (int r = 0; r < 16; ++r) part[r & 3] += v[r];
               }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&b_empty[bs]);
+            if (x3) {
+              // dy boxes stay as they are (hi = what the tensor core reads of them); lo = v - trunc(v) goes next to them
+              // (rows past the tensor were zero-filled: lo = 0)
+              const uint32_t bst = b_ring_a + (uint32_t)(bs * WG_B_STAGE_BYTES) + my_off;
+              for (int g = 0; g < nbx; ++g) {
+                float4 w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = lds128(bst + (uint32_t)(g * WG_BOX_BYTES) + 2048u * i);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  sts128(bst + (uint32_t)prm.b_half + (uint32_t)(g * WG_BOX_BYTES) + 2048u * i,
+                         make_float4(w[i].x - trunc_tf32(w[i].x), w[i].y - trunc_tf32(w[i].y), w[i].z - trunc_tf32(w[i].z),
+                                     w[i].w - trunc_tf32(w[i].w)));
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&b_ready[bs]);
+            } else {
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&b_empty[bs]);
+            }
             if (++bs == WG_B_STAGES) { bs = 0; bph ^= 1; }
           }
-          if (xf) {
+          if (xf || x3) {
             for (int mg = 0; mg < groups; ++mg) {
               const int tl_n = min(prm.tpm, ntap - mg * prm.tpm);
               mbar_wait(&a_full[as], aph);
@@ -1306,14 +1441,31 @@ __global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __gri
 #pragma unroll
                   for (int i = 0; i < 4; ++i)
                     if (valid[i]) w[i] = lds128(box + 2048u * i);
+                  if (x3) {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    if (valid[i]) {
-                      w[i].x = round_tf32(fmaxf(fmaf(w[i].x, sc.x, sh.x), 0.f));
-                      w[i].y = round_tf32(fmaxf(fmaf(w[i].y, sc.y, sh.y), 0.f));
-                      w[i].z = round_tf32(fmaxf(fmaf(w[i].z, sc.z, sh.z), 0.f));
-                      w[i].w = round_tf32(fmaxf(fmaf(w[i].w, sc.w, sh.w), 0.f));
-                      sts128(box + 2048u * i, w[i]);
+                    for (int i = 0; i < 4; ++i) {
+                      float4 lo = make_float4(0.f, 0.f, 0.f, 0.f);        // zero-filled rows stay zero in both halves
+                      if (valid[i]) {
+                        if (xf) {
+                          w[i].x = fmaxf(fmaf(w[i].x, sc.x, sh.x), 0.f); w[i].y = fmaxf(fmaf(w[i].y, sc.y, sh.y), 0.f);
+                          w[i].z = fmaxf(fmaf(w[i].z, sc.z, sh.z), 0.f); w[i].w = fmaxf(fmaf(w[i].w, sc.w, sh.w), 0.f);
+                        }
+                        if (xf) sts128(box + 2048u * i, w[i]);
+                        lo = make_float4(w[i].x - trunc_tf32(w[i].x), w[i].y - trunc_tf32(w[i].y), w[i].z - trunc_tf32(w[i].z),
+                                         w[i].w - trunc_tf32(w[i].w));
+                      }
+                      sts128(box + (uint32_t)prm.a_half + 2048u * i, lo);
+                    }
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      if (valid[i]) {
+                        w[i].x = round_tf32(fmaxf(fmaf(w[i].x, sc.x, sh.x), 0.f));
+                        w[i].y = round_tf32(fmaxf(fmaf(w[i].y, sc.y, sh.y), 0.f));
+                        w[i].z = round_tf32(fmaxf(fmaf(w[i].z, sc.z, sh.z), 0.f));
+                        w[i].w = round_tf32(fmaxf(fmaf(w[i].w, sc.w, sh.w), 0.f));
+                        sts128(box + 2048u * i, w[i]);
+                      }
                     }
                   }
                 }
@@ -1381,6 +1533,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   prm.dw = a.dw; prm.dbias = a.dbias;
   prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = ktot; prm.taps = a.taps; prm.S = a.S;
   prm.seg_k = a.kpad; prm.lddw = a.lddw ? a.lddw : ktot;
+  prm.x3 = a.x3;
   prm.xf_save = a.xf_save; prm.xf_C = a.xf_C;
   prm.log2S = 0;
   while ((1 << prm.log2S) < a.S) ++prm.log2S;
@@ -1419,7 +1572,19 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   const int a_boxes = prm.tpm * prm.kb > 4 ? 4 : prm.tpm * prm.kb;
   prm.b_stage_bytes = (N / 32) * WG_BOX_BYTES;
   bool two_ctas = false;
-  if (variant != 0 && a_boxes == 1) {
+  if (a.x3) {
+    // 3xTF32: every stage holds the hi boxes followed by their lo halves: full 4-box A slots (64 KB per stage, two
+    // stages) and as many dy stages as fit behind them
+    prm.a_half = 4 * WG_BOX_BYTES;
+    prm.b_half = prm.b_stage_bytes;
+    prm.a_stage_bytes = 2 * prm.a_half;
+    prm.b_stage_bytes = 2 * prm.b_half;
+    prm.a_lbo = WG_BOX_BYTES;
+    prm.a_stages = 2;
+    prm.b_stages = (WG_RING_BYTES - prm.a_stages * prm.a_stage_bytes) / prm.b_stage_bytes;
+    if (prm.b_stages > 4) prm.b_stages = 4;
+    prm.ring_bytes = prm.a_stages * prm.a_stage_bytes + prm.b_stages * prm.b_stage_bytes;
+  } else if (variant != 0 && a_boxes == 1) {
     // compact: 8 KB A stages, the four groups alias the one box; small enough for two CTAs per SM
     prm.a_stage_bytes = WG_BOX_BYTES;
     prm.a_lbo = 0;

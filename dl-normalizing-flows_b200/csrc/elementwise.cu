@@ -1119,7 +1119,8 @@ __device__ __forceinline__ float block_sum(float v, float* sm) {
 // memory so that BOTH layouts are written with full 128-byte rows -- wf[tap][co][ci] along ci, the
 // transposed and tap-flipped wb[taps-1-tap][ci][co] along co.  Padding rows / columns are written as zeros.
 constexpr int kWnTile = 32;
-__global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase, int rnd) {
+__global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __restrict__ jobs, float* __restrict__ wbase, int rnd,
+                                                             size_t lo_delta) {
   extern __shared__ float wn_sm[];               // [32][32 * taps + 1] slab, then f[32]
   const WnJob j = jobs[blockIdx.y];
   const int co0 = blockIdx.x * kWnTile;
@@ -1156,25 +1157,32 @@ __global__ void __launch_bounds__(256) weightnorm_fwd_kernel(const WnJob* __rest
       // wf[tap][co0 + r][ci0 + lane]: a warp writes one 128-byte row
       for (int r = warp; r < kWnTile; r += 8) {
         const int co = co0 + r;
-        if (co < j.npad_f)
-          wf[((int64_t)tap * j.npad_f + co) * ldf + ci0 + lane] = maybe_round(slab[r * pitch + lane * taps + tap] * f[r], rnd);
+        if (co < j.npad_f) {
+          const float w = maybe_round(slab[r * pitch + lane * taps + tap] * f[r], rnd);
+          const int64_t o = ((int64_t)tap * j.npad_f + co) * ldf + ci0 + lane;
+          wf[o] = w;
+          if (lo_delta) wf[o + lo_delta] = w - trunc_tf32(w);
+        }
       }
       // wb[taps-1-tap][ci0 + i][co0 + lane]
       for (int i = warp; i < kWnTile; i += 8) {
         const int ci = ci0 + i;
-        if (ci < j.npad_b)
-          wb[((int64_t)(taps - 1 - tap) * j.npad_b + ci) * j.kpad_b + co0 + lane] =
-              maybe_round(slab[lane * pitch + i * taps + tap] * f[lane], rnd);
+        if (ci < j.npad_b) {
+          const float w = maybe_round(slab[lane * pitch + i * taps + tap] * f[lane], rnd);
+          const int64_t o = ((int64_t)(taps - 1 - tap) * j.npad_b + ci) * j.kpad_b + co0 + lane;
+          wb[o] = w;
+          if (lo_delta) wb[o + lo_delta] = w - trunc_tf32(w);
+        }
       }
     }
   }
 }
 int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
-                     cudaStream_t st) {
+                     cudaStream_t st, size_t lo_delta) {
   if (njobs == 0) return RNVP_OK;
   // the slab is sized for 3x3 kernels (the only other tap count is 1)
   const int smem = (kWnTile * (kWnTile * 9 + 1) + kWnTile) * (int)sizeof(float);
-  weightnorm_fwd_kernel<<<dim3(ceil_div(pad_to(max_cout, 32), kWnTile), njobs), 256, smem, st>>>(jobs_dev, wbase, tf32_round);
+  weightnorm_fwd_kernel<<<dim3(ceil_div(pad_to(max_cout, 32), kWnTile), njobs), 256, smem, st>>>(jobs_dev, wbase, tf32_round, lo_delta);
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

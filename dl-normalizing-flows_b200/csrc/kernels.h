@@ -113,8 +113,9 @@ struct WnJob {
   size_t dbias_src_off;
 };
 // writes every element of wf and wb (zero in the padding), so the arena needs no clearing
+// lo_delta != 0 (3xTF32 tier): also write lo = w - trunc_tf32(w) of both layouts lo_delta floats further on
 int k_weightnorm_fwd(const WnJob* jobs_dev, int njobs, int max_cout, float* wbase, int tf32_round,
-                     cudaStream_t st);
+                     cudaStream_t st, size_t lo_delta = 0);
 int k_weightnorm_bwd(const WnJob* jobs_dev, int njobs, int max_cout, const float* wbase,
                      const float* dwbase, cudaStream_t st);
 
@@ -225,6 +226,10 @@ struct ConvArgs {
   int segs = 1;
   size_t seg_stride = 0;
   int ldw = 0;
+  // fp32-accurate tensor-core tier ("3xTF32", conv_tc.cu): split operands, three MMAs per K step.  w_lo_delta = distance
+  // in floats from w to its lo copy (w - trunc_tf32(w), same layout), written by the weight-norm kernel.
+  int x3 = 0;
+  size_t w_lo_delta = 0;
 };
 int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
@@ -244,6 +249,7 @@ struct WgradArgs {
   int segs = 1;
   size_t seg_stride = 0;
   int lddw = 0;
+  int x3 = 0;          // 3xTF32: x and dy boxes are split into hi / lo in shared memory, three MMAs per K step
 };
 bool wgrad_tf32_prologue_ok(const WgradArgs& a);
 int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st);

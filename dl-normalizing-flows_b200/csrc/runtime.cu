@@ -313,6 +313,10 @@ int build_plan(rnvp_plan* p, const SingleSpec* single = nullptr) {
   return RNVP_OK;
 }
 
+// math tiers: the tensor-core kernels serve TF32 (operands rounded to TF32 by their producers) and TF32X3 (3xTF32
+// split operands, nothing rounded: the fp32-accurate tensor-core tier); FP32 is the CUDA-core reference tier
+inline bool tc_tier(const rnvp_plan* p) { return p->math != RNVP_MATH_FP32; }
+inline bool x3_tier(const rnvp_plan* p) { return p->math == RNVP_MATH_TF32X3; }
 bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d);
 bool bn_fused(const rnvp_plan* p, const CouplingDesc& d, int bi);
 
@@ -347,7 +351,7 @@ Layout compute_layout(const rnvp_plan* p, int B, int mode) {
   Layout L{};
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 1024); return r; };
-  L.weights = take(p->weight_floats * 4);
+  L.weights = take(p->weight_floats * 4 * (x3_tier(p) ? 2 : 1));     // 3xTF32: the lo copy follows the weights
   L.dw = take(mode >= 1 ? p->dw_floats * 4 : 0);
   L.accum = take((32 + 2 * (size_t)B) * 8);
   L.stats_f_bytes = p->stats_f_doubles * 8;
@@ -436,7 +440,7 @@ bool xform_enabled() {
 }
 // true when the tensor-core kernels of coupling `d` can apply a BN to their operand tiles (shape / tier check)
 bool cpl_xf(const rnvp_plan* p, const CouplingDesc& d) {
-  if (p->math != RNVP_MATH_TF32 || !xform_enabled()) return false;
+  if (!tc_tier(p) || !xform_enabled()) return false;
   ConvArgs a{};
   a.S = d.S; a.kpad = d.ldD; a.ldy = d.ldD; a.n = d.D;
   WgradArgs w{};
@@ -464,7 +468,7 @@ bool skip_fused(const rnvp_plan* p, const CouplingDesc& d, int B, int mode) {
     const char* e = getenv("RNVP_SKIP_FUSED");
     on = (e && e[0] == '0') ? 0 : 1;
   }
-  if (!on || p->math != RNVP_MATH_TF32) return false;
+  if (!on || !tc_tier(p)) return false;
   ConvArgs a{};
   a.S = d.S; a.kpad = d.ldD; a.ldy = d.ldD; a.n = d.D;
   WgradArgs w{};
@@ -530,6 +534,7 @@ ConvArgs conv_args(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x,
   a.npad = dgrad ? cv.npad_b : cv.npad;
   a.taps = cv.taps; a.ldy = ldy;
   a.ldw = dgrad ? cv.kpad_b : cv.ld_f;
+  if (x3_tier(c.p)) { a.x3 = 1; a.w_lo_delta = c.p->weight_floats; }
   return a;
 }
 
@@ -541,7 +546,7 @@ int run_conv(const Ctx& c, const ConvDesc& cv, bool dgrad, const float* x, int S
   // y is read raw by later conv MMAs: round it where it is produced (tensor-core tier only)
   a.round_out = operand_out && c.p->math == RNVP_MATH_TF32;
   if (post_save) { a.post_scale = post_save + 2 * a.n; a.post_shift = post_save + 3 * a.n; }
-  return c.p->math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
+  return tc_tier(c.p) ? k_conv_fwd_tf32(a, c.st) : k_conv_fwd_fp32(a, c.st);
 }
 // conv whose input is relu(bn_bi(x_raw)): BN prologue inside the tensor-core kernel
 int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, double count, const float* x_raw, int S,
@@ -552,7 +557,7 @@ int run_conv_bn(const Ctx& c, int ci, const ConvDesc& cv, int bi, int training, 
   const BnDesc& b = d.bns[bi];
   ProfScope ps(PROF_CONV, S, cv.taps, cv.cin, cv.cout, c.st);
   ConvArgs a = conv_args(c, cv, false, x_raw, S, y, ldy, bias, res, stats);
-  a.round_out = operand_out;
+  a.round_out = operand_out && p->math == RNVP_MATH_TF32;
   if (post_save) { a.post_scale = post_save + 2 * a.n; a.post_shift = post_save + 3 * a.n; }
   BnPrologue x{};
   x.mode = training ? 1 : 0; x.C = b.C; x.sums = c.sf(b.sf); x.count = count;
@@ -593,7 +598,8 @@ int run_wgrad(const Ctx& c, const ConvDesc& cv, const float* x, const float* dy,
   a.xf_save = xf_save; a.xf_C = xf_C;
   a.B = c.B; a.S = S; a.kpad = cv.kpad; a.n = cv.cout; a.npad = cv.npad; a.taps = cv.taps; a.lddy = lddy;
   a.lddw = cv.ld_dw;
-  return c.p->math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, c.wst) : k_conv_wgrad_fp32(a, c.wst);
+  a.x3 = x3_tier(c.p);
+  return tc_tier(c.p) ? k_conv_wgrad_tf32(a, c.wst) : k_conv_wgrad_fp32(a, c.wst);
 }
 
 // ------------------------------------------------------------------------------------
@@ -765,6 +771,7 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     a.x = c.act(ci, A.a[0]); a.dy = DO; a.dw = c.dw() + d.dwskip_off; a.dbias = c.dw() + d.dbskip_off;
     a.B = c.B; a.S = S; a.kpad = ld; a.n = d.D; a.npad = cv[1].npad; a.taps = 1; a.lddy = ld;
     a.segs = R + 1; a.seg_stride = A.a[1] - A.a[0]; a.lddw = (R + 1) * ld;
+    a.x3 = x3_tier(p);
     RNVP_TRY(k_conv_wgrad_tf32(a, c.wst));
   }
   const float* DA = nullptr;               // d(a_{i+1}) accumulated so far
@@ -919,7 +926,7 @@ int coupling_backward(const Ctx& c, int ci, const float* dy, const float* dll, f
 int materialize_weights(const Ctx& c, int first_job, int njobs, int first_cpl, int ncpl) {
   RNVP_TRY(k_bias_sum(c.p->d_biasjobs + first_cpl, ncpl, c.weights(), c.st));
   return k_weightnorm_fwd(c.p->d_jobs + first_job, njobs, c.p->max_cout, c.weights(),
-                          c.p->math == RNVP_MATH_TF32, c.st);
+                          c.p->math == RNVP_MATH_TF32, c.st, x3_tier(c.p) ? c.p->weight_floats : 0);
 }
 // eval mode: the batch norms are fixed affine maps; their (scale, shift) go into the `save` arena once per call
 int eval_bn_coefs(const Ctx& c) {
@@ -1068,7 +1075,7 @@ unsigned long long rnvp_plan_forward_generation(const rnvp_plan* p) { return p ?
 
 int rnvp_plan_set_math(rnvp_plan* p, int math) {
   RNVP_REQUIRE(p, "null plan");
-  RNVP_REQUIRE(math == RNVP_MATH_FP32 || math == RNVP_MATH_TF32, "unknown math mode %d", math);
+  RNVP_REQUIRE(math == RNVP_MATH_FP32 || math == RNVP_MATH_TF32 || math == RNVP_MATH_TF32X3, "unknown math mode %d", math);
   p->math = math;
   return RNVP_OK;
 }
@@ -1559,14 +1566,19 @@ int rnvp_conv_forward(const float* x, const float* wf, const float* bias, const 
   ConvArgs a{};
   a.x = x; a.w = wf; a.bias = bias; a.res = res; a.y = y; a.stats = stats;
   a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.ldy = ldy;
-  return math == RNVP_MATH_TF32 ? k_conv_fwd_tf32(a, (cudaStream_t)stream) : k_conv_fwd_fp32(a, (cudaStream_t)stream);
+  if (math == RNVP_MATH_TF32X3) {        // wf holds [w | w - trunc_tf32(w)], each taps * npad * kpad floats
+    a.x3 = 1;
+    a.w_lo_delta = (size_t)a.taps * npad * kpad;
+  }
+  return math != RNVP_MATH_FP32 ? k_conv_fwd_tf32(a, (cudaStream_t)stream) : k_conv_fwd_fp32(a, (cudaStream_t)stream);
 }
 int rnvp_conv_wgrad(const float* x, const float* dy, float* dwf, float* dbias, int B, int S, int kpad, int n,
                     int npad, int ksize, int lddy, int math, void* stream) {
   WgradArgs a{};
   a.x = x; a.dy = dy; a.dw = dwf; a.dbias = dbias;
   a.B = B; a.S = S; a.kpad = kpad; a.n = n; a.npad = npad; a.taps = ksize * ksize; a.lddy = lddy;
-  return math == RNVP_MATH_TF32 ? k_conv_wgrad_tf32(a, (cudaStream_t)stream) : k_conv_wgrad_fp32(a, (cudaStream_t)stream);
+  a.x3 = math == RNVP_MATH_TF32X3;
+  return math != RNVP_MATH_FP32 ? k_conv_wgrad_tf32(a, (cudaStream_t)stream) : k_conv_wgrad_fp32(a, (cudaStream_t)stream);
 }
 
 int rnvp_conv_forward_bn(const float* x_raw, const float* wf, const float* bias, const float* res, float* y,

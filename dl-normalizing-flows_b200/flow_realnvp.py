@@ -118,7 +118,7 @@ class RealNVP(nn.Module):
         import rnvp_cabi
         if not self._native:
             return
-        self.engine().set_math({"fp32": rnvp_cabi.MATH_FP32, "tf32": rnvp_cabi.MATH_TF32}[mode])
+        self.engine().set_math(rnvp_cabi.MATH_BY_NAME[mode])
         for cpl in self._couplings():
             cpl.set_math(mode)
 

@@ -174,7 +174,7 @@ class AbstractCoupling(nn.Module):
     def set_math(self, mode):
         """'tf32' / 'fp32' arithmetic tier for this module's stand-alone calls (None = default)."""
         import rnvp_cabi
-        self._math = None if mode is None else {"fp32": rnvp_cabi.MATH_FP32, "tf32": rnvp_cabi.MATH_TF32}[mode]
+        self._math = None if mode is None else rnvp_cabi.MATH_BY_NAME[mode]
         for e in self._all_engines():
             e.set_math(_eng._DEFAULT_MATH if self._math is None else self._math)
 

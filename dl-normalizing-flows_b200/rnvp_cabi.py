@@ -13,6 +13,8 @@ LIB_PATH = os.environ.get("RNVP_B200_LIB", os.path.join(_HERE, "librnvp_b200.so"
 
 MATH_FP32 = 0
 MATH_TF32 = 1
+MATH_TF32X3 = 2          # 3xTF32 split operands on the tensor cores: the fp32-accurate tier (include/rnvp.h)
+MATH_BY_NAME = {"fp32": MATH_FP32, "tf32": MATH_TF32, "tf32x3": MATH_TF32X3}
 
 
 class RnvpError(RuntimeError):

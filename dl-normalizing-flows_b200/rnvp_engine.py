@@ -29,7 +29,7 @@ _DEFAULT_MATH = cabi.MATH_TF32
 def set_default_math(mode: str) -> None:
     """'fp32' (CUDA-core, 1e-5 tier) or 'tf32' (tcgen05 tensor cores, 1e-3 tier)."""
     global _DEFAULT_MATH
-    _DEFAULT_MATH = {"fp32": cabi.MATH_FP32, "tf32": cabi.MATH_TF32}[mode]
+    _DEFAULT_MATH = cabi.MATH_BY_NAME[mode]
 
 
 def _resolve(module: nn.Module, dotted: str):

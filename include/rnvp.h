@@ -43,7 +43,9 @@ typedef enum {
 /* conv arithmetic tier (SURVEY.md 7 "precision tiers") */
 typedef enum {
   RNVP_MATH_FP32 = 0,        /* CUDA-core fp32 FMA implicit GEMM (1e-5 tier, reconstruction gate) */
-  RNVP_MATH_TF32 = 1         /* tcgen05 kind::tf32, fp32 accumulate in TMEM (1e-3 tier, throughput) */
+  RNVP_MATH_TF32 = 1,        /* tcgen05 kind::tf32, fp32 accumulate in TMEM (1e-3 tier, throughput) */
+  RNVP_MATH_TF32X3 = 2       /* the same tensor-core kernels with split operands ("3xTF32": hi*hi + lo*hi + hi*lo, three
+                                MMAs per K step, nothing rounded): fp32-class accuracy (1e-5 tier) on tcgen05 */
 } rnvp_math;
 
 /* RealNVP(channels, image_size, prior, hps): flow_realnvp.py:36-95, utils.py:78-93.

@@ -26,7 +26,13 @@ def build(pkg, c, state, math):
 # end-to-end gradients: global rel-L2 vs the reference (its own fp32-vs-fp64 floor is 5.5e-3);
 # under TF32 operands the 28-deep train-mode stack is chaotic at these tiny test points, so that tier
 # only checks the direction (cosine >= ~0.87) -- its kernels are pinned per op in test_gpu_ops.py
-TIERS = [("fp32", 1e-5, 5e-4, 2e-2), ("tf32", 1e-3, 0.3, 0.5)]
+# "tf32x3" = the same tensor-core kernels with 3xTF32 split operands: held to the fp32 tier's gates, except in eval
+# mode.  There the running statistics do not re-centre the activations layer by layer, and the tensor core's fp32
+# accumulation TRUNCATES after every MMA (a bias towards zero that batch statistics would remove): measured
+# 1.0e-5 ... 6.1e-5 on the eval log-likelihood (3e-7 in train mode), against 8e-7 for the CUDA-core fp32 tier.
+TIERS = [("fp32", 1e-5, 5e-4, 2e-2), ("tf32x3", 1e-5, 5e-4, 2e-2), ("tf32", 1e-3, 0.3, 0.5)]
+EXACT = ("fp32", "tf32x3")
+EVAL_LL_TOL = {"fp32": 1e-5, "tf32x3": 1e-4, "tf32": 5e-2}
 
 
 @pytest.mark.parametrize("math,ll_tol,z_tol,g_tol", TIERS)
@@ -50,7 +56,7 @@ def test_golden_model(pkg, golden_dir, name, math, ll_tol, z_tol, g_tol):
     assert set(got) == set(fix["train_grads"])
     grel, worst, wk = compare_grads(got, fix["train_grads"], fix["train_grad_norms"])
     assert grel < g_tol, (grel, worst, wk)
-    if math == "fp32":
+    if math in EXACT:
         assert worst < 0.05, (worst, wk)
     sd = m.state_dict()
     for k, v in fix["state_after_train"].items():
@@ -64,13 +70,13 @@ def test_golden_model(pkg, golden_dir, name, math, ll_tol, z_tol, g_tol):
     with torch.no_grad():
         z, J = m2.f(x)
     assert rel(J.sum((1, 2, 3)), fix["train_J"].sum((1, 2, 3))) < ll_tol
-    if math == "fp32":
+    if math in EXACT:
         assert rel(z, fix["train_z"]) < z_tol and rel(J, fix["train_J"]) < z_tol
     m3 = build(pkg, c, st0, math)
     m3.train()
     z3, ld3, ll3 = m3.latent(x)
     assert rel(ld3, fix["train_J"].sum((1, 2, 3))) < ll_tol
-    if math == "fp32":
+    if math in EXACT:
         assert rel(z3, fix["train_z"]) < z_tol
     # ---- eval mode --------------------------------------------------------------------------------
     m4 = build(pkg, c, st0, math)
@@ -80,9 +86,9 @@ def test_golden_model(pkg, golden_dir, name, math, ll_tol, z_tol, g_tol):
         # the fixture's running statistics are random, i.e. an ill-conditioned eval point:
         # gated tightly in the fp32 tier only; the TF32 eval gate uses converged statistics
         # (test_cfg_a_against_oracle, test_survey_operating_point)
-        assert rel(lle, fix["eval_ll"]) < (ll_tol if math == "fp32" else 5e-2), rel(lle, fix["eval_ll"])
+        assert rel(lle, fix["eval_ll"]) < EVAL_LL_TOL[math], rel(lle, fix["eval_ll"])
         xs = m4.g(fix["z_sample"].to(DEV))
-        if math == "fp32":
+        if math in EXACT:
             assert rel(xs, fix["eval_g"]) < z_tol
             ze, _, _ = m4.latent(x)
             rec = m4.g(ze)
@@ -160,7 +166,7 @@ def test_input_gradient(pkg, golden_dir):
     assert rel(xd.grad, xr.grad) < 2e-3, rel(xd.grad, xr.grad)
 
 
-@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("tf32", 1e-3)])
 def test_cfg_a_against_oracle(pkg, math, tol):
     """BASELINE config (64x64x3, base 32, 4 blocks) at a batch the CPU oracle finishes in seconds."""
     B = 4
@@ -235,7 +241,7 @@ def test_full_size_properties(pkg):
     assert rel(ll_t, ll_f) < 1e-3 and rel(ld_t, ld_f) < 1e-3, (rel(ll_t, ll_f), rel(ld_t, ld_f))
 
 
-@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32", 1e-3)])
+@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("tf32", 1e-3)])
 def test_survey_operating_point(pkg, math, tol):
     """The parity gate of the north star at the operating point SURVEY.md 8d prescribes: the
     reference's default initialisation under torch.manual_seed(0) (bit-identical here, see
@@ -276,7 +282,7 @@ def test_survey_operating_point(pkg, math, tol):
         ll_e = ora2.log_prob(x)
         ll_de, _ = m(x.to(DEV))
     print(f"[{math}] train ll {rel(ll_d, lp + ld):.2e} logdet {rel(ld_d, ld):.2e}; eval ll {rel(ll_de, ll_e):.2e}")
-    assert rel(ll_de, ll_e) < (1e-5 if math == "fp32" else 5e-2)
+    assert rel(ll_de, ll_e) < EVAL_LL_TOL[math]
 
 
 def test_lean_and_fast_training_modes_agree(pkg, golden_dir):

@@ -28,6 +28,9 @@ for s in "$@"; do
     targetsenv:*) name=$(echo $s | cut -d: -f2); envs=$(echo $s | cut -d: -f3 | tr ',' ' ')
       env $envs TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets_${name}.log 2>&1 ;;
     hosttime) timeout 300 python tools/host_time.py > $OUT/${TAG}_hosttime.log 2>&1; B=64 timeout 300 python tools/host_time.py >> $OUT/${TAG}_hosttime.log 2>&1 ;;
+    x3ops) timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x --timeout 300 -k "tf32x3" > $OUT/${TAG}_x3ops.log 2>&1 ;;
+    x3rest) timeout 900 python -m pytest tests/test_gpu_coupling.py tests/test_gpu_flow.py tests/test_gpu_api.py -m gpu -q --timeout 600 -k "tf32x3" > $OUT/${TAG}_x3rest.log 2>&1 ;;
+    x3bench) timeout 900 python bench.py --math tf32x3 --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager > $OUT/${TAG}_x3bench.json 2> $OUT/${TAG}_x3bench.err ;;
     targets) TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets.log 2>&1 ;;
     ncu_targets) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_(fwd|wgrad)_tf32" -c 27 \
                    -o $OUT/${TAG}_targets python tools/ncu_targets.py > $OUT/${TAG}_ncu_targets.log 2>&1 ;;

@@ -346,11 +346,16 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr int B_TILE_BYTES = BN * 128;
   constexpr int HALF_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr int STAGE_BYTES = X3 ? 2 * HALF_BYTES : HALF_BYTES;
-  // 3xTF32 keeps the two small products (lo*hi, hi*lo) in their own accumulator next to the main one: the tensor core
-  // truncates after every accumulation step, and this way the main accumulator takes 4 such steps per chunk instead
-  // of 12 (the lo accumulator's truncation is relative to values 2^-11 times smaller); the epilogue adds the two.
-  constexpr int ACC_COLS = X3 ? 2 * BN : BN;              // columns of one accumulator buffer: [main | lo]
-  constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;
+  // The tensor core TRUNCATES its fp32 accumulator after every accumulation step -- a bias towards zero that grows with
+  // the number of steps and is what bounds the accuracy of the 3xTF32 tier.  So that tier (a) keeps the two small
+  // products (lo*hi, hi*lo) in their own accumulator (its truncation is relative to values 2^-11 times smaller) and
+  // (b) deals the hi*hi products of successive chunks round-robin over NACC partial accumulators; the epilogue adds
+  // them up in registers (round to nearest).  One buffer = [main 0 | .. | main NACC-1 | lo]; the 128-wide tile then
+  // fills the 512 TMEM columns with ONE buffer (no overlap of a tile's epilogue with the next tile's MMAs).
+  constexpr int NACC = X3 ? 3 : 1;
+  constexpr int ACC_COLS = X3 ? (NACC + 1) * BN : BN;
+  constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;
+  constexpr int TMEM_COLS = NBUF * ACC_COLS < 32 ? 32 : NBUF * ACC_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t smem_a = smem_u32(smem);                            // shared-window address of the ring
@@ -459,8 +464,8 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t phase = 0;
     uint64_t soff = 0;                                       // (s * STAGE_BYTES) >> 4, added to the address field
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++ti) {
-      const int as = ti & 1;
-      mbar_wait(&acc_empty[as], ((ti >> 1) & 1) ^ 1);       // epilogue drained this accumulator
+      const int as = ti % NBUF;
+      mbar_wait(&acc_empty[as], ((ti / NBUF) & 1) ^ 1);     // epilogue drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(as * ACC_COLS);
       for (int it = 0; it < iters; ++it) {
@@ -471,10 +476,12 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           if constexpr (X3) {
             constexpr uint64_t LO = (uint64_t)(HALF_BYTES >> 4);   // address-field distance of the lo tiles
 #pragma unroll
+            const uint32_t d_main = d_tmem + (uint32_t)((it % NACC) * BN);                  // partial accumulator
+#pragma unroll
             for (int k = 0; k < 8; k += 2) {
-              umma_tf32(d_tmem + BN, ad + LO + k, bd + k, idesc, (it != 0) | (k != 0));     // lo accumulator
-              umma_tf32(d_tmem + BN, ad + k, bd + LO + k, idesc, 1);
-              umma_tf32(d_tmem, ad + k, bd + k, idesc, (it != 0) | (k != 0));               // main accumulator
+              umma_tf32(d_tmem + NACC * BN, ad + LO + k, bd + k, idesc, (it != 0) | (k != 0));     // lo accumulator
+              umma_tf32(d_tmem + NACC * BN, ad + k, bd + LO + k, idesc, 1);
+              umma_tf32(d_main, ad + k, bd + k, idesc, (it >= NACC) | (k != 0));
             }
           } else {
             umma_tf32(d_tmem, ad, bd, idesc, it != 0);        // 4 x (K = 8 fp32 = 32 bytes) per 128-byte row
@@ -605,11 +612,13 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int ti = 0;
     for (int tt = blockIdx.x; tt < num_tiles; tt += gridDim.x, ++ti) {
       const int t = prm.rev ? num_tiles - 1 - tt : tt;
-      const int as = ti & 1;
+      const int as = ti % NBUF;
       const int m_tile = t / prm.n_tiles, n0 = (t % prm.n_tiles) * BN;
       const int prow0 = m_tile * 128 + q * 32;
       const bool pvalid = prow0 + lane < prm.P;
-      mbar_wait(&acc_full[as], (ti >> 1) & 1);
+      const int nacc = iters < NACC ? iters : NACC;          // partial accumulators this tile's chunks have written
+      (void)nacc;
+      mbar_wait(&acc_full[as], (ti / NBUF) & 1);
       tc_fence_after();
       if constexpr (CPL) {
         // ---- the coupling itself, on the accumulator of the s/t net's out conv (modules_realnvp.py:277-301,
@@ -632,11 +641,14 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tmem_ld_32x8(tb + (uint32_t)cb, tv);
           tmem_ld_32x8(tb + (uint32_t)(g.cio + cb), lv);
           if constexpr (X3) {
-            float t2[8], l2[8];
-            tmem_ld_32x8(tb + (uint32_t)(BN + cb), t2);
-            tmem_ld_32x8(tb + (uint32_t)(BN + g.cio + cb), l2);
+            for (int a = 1; a <= NACC; ++a) {                       // the other partials, then the lo accumulator
+              if (a < NACC && a >= nacc) continue;
+              float t2[8], l2[8];
+              tmem_ld_32x8(tb + (uint32_t)(a * BN + cb), t2);
+              tmem_ld_32x8(tb + (uint32_t)(a * BN + g.cio + cb), l2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { tv[j] += t2[j]; lv[j] += l2[j]; }
+              for (int j = 0; j < 8; ++j) { tv[j] += t2[j]; lv[j] += l2[j]; }
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -705,12 +717,15 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + c0), v);
         if constexpr (X3) {
+          for (int a = 1; a <= NACC; ++a) {                         // the other partials, then the lo accumulator
+            if (a < NACC && a >= nacc) continue;
 #pragma unroll
-          for (int j8 = 0; j8 < 32; j8 += 8) {
-            float v2[8];
-            tmem_ld_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + BN + c0 + j8), v2);
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              float v2[8];
+              tmem_ld_32x8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + a * BN + c0 + j8), v2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j8 + j] += v2[j];
+              for (int j = 0; j < 8; ++j) v[j8 + j] += v2[j];
+            }
           }
         }
         if (prm.bias) {
@@ -1037,7 +1052,8 @@ static int launch_fwd(const ConvArgs& a, ConvTcParams prm, cudaStream_t st) {
   // (cudaOccupancyMaxActiveBlocksPerMultiprocessor under-reports this kernel: it answered 1 where 2 fit)
   int ctas = (228 * 1024) / (smem + ki.static_smem + 1024);
   if (ctas > ki.by_regs) ctas = ki.by_regs;
-  constexpr int tmem_cols = (X3 ? 4 : 2) * BN < 32 ? 32 : (X3 ? 4 : 2) * BN;
+  constexpr int acc_cols = X3 ? 4 * BN : BN;                 // kernel: [3 partial mains | lo] per buffer in the 3xTF32 tier
+  constexpr int tmem_cols = (2 * acc_cols <= 512 ? 2 : 1) * acc_cols < 32 ? 32 : (2 * acc_cols <= 512 ? 2 : 1) * acc_cols;
   if (ctas > 512 / tmem_cols) ctas = 512 / tmem_cols;
   if (ctas < 1) ctas = 1;
   ctas = env_int("RNVP_TC_CTAS", 1, 8, ctas);

@@ -125,8 +125,11 @@ def _conv_case(pkg, B, S, cin, cout, k, math, seed=0, with_res=True):
     check(lib.rnvp_conv_forward(ptr(xn), ptr(wf), ptr(bias_d), ptr(y) if with_res else None, ptr(y), ptr(stats),
                                 B, S, kpad, cout, npad, k, ldy, math, _stream()))
     got = y[..., :cout].permute(0, 3, 1, 2).cpu()
-    # 3xTF32: the tensor core truncates its fp32 accumulator after every MMA: up to 1.3e-5 of max at K = 4608
-    tol = (1e-5 if math == 0 else 2.5e-5) if exact else 3e-3
+    # 3xTF32 (measured 3e-7 ... 4.1e-6 of max, the largest at K = 4608: the tensor core truncates its fp32 accumulator
+    # after every MMA, which is why that tier spreads the products over partial accumulators) meets the fp32 tolerance
+    tol = 1e-5 if exact else 3e-3
+    if math == 2:
+        print(f"[tf32x3] conv {B}x{S}x{S} {cin}->{cout} k{k}: {rel(got, y_ref):.2e} of max")
     assert rel(got, y_ref) < tol, (rel(got, y_ref), B, S, cin, cout, k)
     s_ref = torch.cat((y_ref.double().sum((0, 2, 3)), (y_ref.double() ** 2).sum((0, 2, 3))))
     assert rel(stats, s_ref) < (tol if exact else 3e-3)
@@ -149,7 +152,9 @@ def _conv_case(pkg, B, S, cin, cout, k, math, seed=0, with_res=True):
     db = torch.zeros(cout, device=DEV)
     check(lib.rnvp_conv_wgrad(ptr(xn), ptr(dyn), ptr(dwf), ptr(db), B, S, kpad, cout, npad, k, kpad_b, math, _stream()))
     got_dw = dwf[:, :cout, :cin].reshape(k, k, cout, cin).permute(2, 3, 0, 1).cpu()
-    assert rel(got_dw, dw_ref) < ((2e-5 if math == 0 else 4e-5) if exact else 3e-3), rel(got_dw, dw_ref)
+    if math == 2:
+        print(f"[tf32x3] dgrad {rel(dx[..., :cin].permute(0, 3, 1, 2), dx_ref):.2e}, wgrad {rel(got_dw, dw_ref):.2e} of max")
+    assert rel(got_dw, dw_ref) < (2e-5 if exact else 3e-3), rel(got_dw, dw_ref)
     assert rel(db, dy.sum((0, 2, 3))) < (2e-5 if exact else 2e-3)
     vr, gr = v.clone().requires_grad_(True), gg.clone().requires_grad_(True)
     wr = vr * (gr / torch.linalg.vector_norm(vr, dim=(1, 2, 3), keepdim=True))

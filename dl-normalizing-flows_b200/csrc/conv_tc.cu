@@ -475,7 +475,6 @@ conv_fwd_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (leader) {
           if constexpr (X3) {
             constexpr uint64_t LO = (uint64_t)(HALF_BYTES >> 4);   // address-field distance of the lo tiles
-#pragma unroll
             const uint32_t d_main = d_tmem + (uint32_t)((it % NACC) * BN);                  // partial accumulator
 #pragma unroll
             for (int k = 0; k < 8; k += 2) {

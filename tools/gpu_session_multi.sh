@@ -22,6 +22,8 @@ for s in $STEPS; do
     weak_plain) run weak_plain "A=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
     weak_fused) run weak_fused "RNVP_DP_FUSED=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
     weak_nofused) run weak_nofused "RNVP_DP_FUSED=0" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
+    weakenv:*) name=$(echo $s | cut -d: -f2); envs=$(echo $s | cut -d: -f3 | tr ',' ' ')
+      run weak_$name "$envs" --steps 10 --warmup 3 --no-cpu-baseline --no-prof ;;
     strong) run strong "A=1" --steps 10 --warmup 3 --no-cpu-baseline --no-prof --global-batch 2048 ;;
     sample_strong) run sample_strong "A=1" --mode sample --steps 5 --warmup 3 --no-cpu-baseline --no-prof --global-batch 4096 ;;
     launcher) PORT=$((PORT+1)); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \

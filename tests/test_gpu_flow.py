@@ -217,6 +217,42 @@ def test_two_scale_config3_shape(pkg):
     assert rel(lld, ll) < 1e-5
 
 
+@pytest.mark.parametrize("math,tol", [("fp32", 1e-5), ("tf32x3", 1e-5), ("tf32", 1e-3)])
+def test_config3_real_width(pkg, math, tol):
+    """BASELINE configs[2] at its real width (32x32x3 -> 16x16x6, two scales, 8 res-blocks, base 64), every tier:
+    per-sample log-likelihood and log-det in train mode, and the gradient direction, against the oracle at a batch
+    the CPU finishes in seconds."""
+    B = 4
+    c = dict(channels=3, image=32, base_dim=64, res_blocks=8, num_scales=2)
+    st0 = O.random_state(3, 32, 64, 8, 2, seed=11, scale=0.2)
+    x_img = O.synthetic_images(B, 3, 32, seed=5)
+    g = torch.Generator().manual_seed(3)
+    x, _ = O.logit_forward(x_img, torch.rand(x_img.shape, generator=g))
+    ost = {k: v.clone().requires_grad_(O.is_trainable(k) and v.is_floating_point()) for k, v in st0.items()}
+    ora = O.RealNVPOracle(ost, 3, 32, 64, 8, 2)
+    z, ld, lp = ora.log_prob_parts(x)
+    (-(lp + ld).mean()).backward()
+    m = build(pkg, c, st0, math)
+    m.train()
+    _, ld_d, ll_d = m.latent(x.to(DEV))
+    print(f"[{math}] config3 real width: ll {rel(ll_d, (lp + ld).detach()):.2e}, logdet {rel(ld_d, ld.detach()):.2e}")
+    assert rel(ld_d, ld.detach()) < tol and rel(ll_d, (lp + ld).detach()) < tol
+    m2 = build(pkg, c, st0, math)
+    m2.train()
+    ll2, _ = m2(x.to(DEV))
+    (-ll2.mean()).backward()
+    num = den = dot = nn_ = 0.0
+    for k, p in m2.named_parameters():
+        if p.grad is None or ost[k].grad is None:
+            continue
+        a_, b_ = p.grad.detach().cpu().double().flatten(), ost[k].grad.double().flatten()
+        num += float(((a_ - b_) ** 2).sum()); den += float((b_ ** 2).sum())
+        dot += float((a_ * b_).sum()); nn_ += float((a_ ** 2).sum())
+    grel, cos = (num / den) ** 0.5, dot / (nn_ * den) ** 0.5
+    print(f"[{math}] config3 real width: gradient rel-L2 {grel:.2e}, cosine {cos:.6f}")
+    assert grel < (2e-2 if math != "tf32" else 0.5) and cos > (0.9995 if math != "tf32" else 0.85)
+
+
 def test_full_size_properties(pkg):
     """BASELINE config 2 size (B=256) -- size-independent properties instead of the oracle:
     g(f(x)) round trip in the fp32 tier, per-sample independence in eval mode, determinism."""

@@ -31,6 +31,11 @@ for s in "$@"; do
     x3ops) timeout 600 python -m pytest tests/test_gpu_ops.py -m gpu -q -x --timeout 300 -k "tf32x3" > $OUT/${TAG}_x3ops.log 2>&1 ;;
     x3rest) timeout 900 python -m pytest tests/test_gpu_coupling.py tests/test_gpu_flow.py tests/test_gpu_api.py -m gpu -q --timeout 600 -k "tf32x3" > $OUT/${TAG}_x3rest.log 2>&1 ;;
     x3bench) timeout 900 python bench.py --math tf32x3 --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager > $OUT/${TAG}_x3bench.json 2> $OUT/${TAG}_x3bench.err ;;
+    refarm) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_refarm.json 2> $OUT/${TAG}_refarm.err ;;
+    c3) timeout 600 python bench.py --config c3 --batch 512 --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-eager > $OUT/${TAG}_c3.json 2> $OUT/${TAG}_c3.err ;;
+    b2048) timeout 900 python bench.py --global-batch 2048 --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-prof > $OUT/${TAG}_b2048.json 2> $OUT/${TAG}_b2048.err ;;
+    traffic) timeout 1500 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 6400 -c 2400 --csv \
+               --log-file $OUT/${TAG}_traffic.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-prof --no-gpu-eager > $OUT/${TAG}_traffic.log 2>&1 ;;
     targets) TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets.log 2>&1 ;;
     ncu_targets) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_(fwd|wgrad)_tf32" -c 27 \
                    -o $OUT/${TAG}_targets python tools/ncu_targets.py > $OUT/${TAG}_ncu_targets.log 2>&1 ;;

@@ -195,7 +195,11 @@ int rnvp_weightnorm_backward(const float* v, const float* g, const float* dwf, f
 /* stride-1 "same" conv as implicit GEMM over NHWC:
  *   y[p, n] = sum_tap sum_k x[p + tap, k] * wf[tap][n][k] (+ bias[n]) (+ res[p, n])
  * x [B,S,S,kpad], wf [taps][npad][kpad], y/res row stride ldy.  stats (2*n
- * doubles, optional) accumulates per-channel sum and sum of squares of y.    */
+ * doubles, optional) accumulates per-channel sum and sum of squares of y.
+ * math = RNVP_MATH_TF32X3: wf holds the weights followed by their lo halves,
+ * [w | w - trunc_tf32(w)], taps*npad*kpad floats each (inside the flow entry
+ * points the weight-norm kernel writes both); rnvp_conv_wgrad needs no extra
+ * operand in that tier (it splits x and dy in shared memory).                 */
 int rnvp_conv_forward(const float* x, const float* wf, const float* bias, const float* res, float* y,
                       double* stats, int B, int S, int kpad, int n, int npad, int ksize, int ldy,
                       int math, void* stream);

@@ -141,9 +141,82 @@ __global__ void __launch_bounds__(kXchgThreads) stats_exchange_kernel(void* cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same exchange without the fence and the flag round trip ("LL": data and flag travel in one store).  Every double
+// is pushed as ONE 16-byte store {lo32, tag, hi32, tag} with tag = the low 32 bits of the sequence number: whatever the
+// fabric does with the 16 bytes, each 8-byte half carries its own tag, so a reader that sees both tags equal to `seq`
+// holds the value -- no __threadfence_system() (a remote-write round trip) before a separate flag store (another
+// one-way trip).  Readers poll their OWN inbox (local memory) element by element and add the world's vectors up in rank
+// order (bit-identical on all ranks).  Slot reuse is safe for the same reason as above: a peer can only start exchange
+// k+2 after finishing k+1, which needs my contribution to k+1, which I push after I have read exchange k.
+// The LL inbox [world][2][cap] x 16 bytes lies behind the flag words of the fenced protocol's inbox.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t xchg_ll_off(int world, int cap) {
+  return (xchg_flag_off(world, cap) + (size_t)(world + 1) * sizeof(unsigned long long) + 15) & ~(size_t)15;
+}
+__global__ void __launch_bounds__(kXchgThreads) stats_exchange_ll_kernel(void* const* __restrict__ peers, int rank, int world,
+                                                                         int cap, double* __restrict__ buf, int n,
+                                                                         unsigned long long seq, int* err) {
+  __shared__ int failed;
+  if (threadIdx.x == 0) failed = 0;
+  __syncthreads();
+  const int slot = (int)(seq & 1ull);
+  const uint32_t tag = (uint32_t)seq;
+  const size_t ll = xchg_ll_off(world, cap);
+  // 1. push {lo, tag, hi, tag} into slot [rank][slot] of every rank's LL inbox (my own included)
+  for (int i = threadIdx.x; i < n; i += kXchgThreads) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(buf[i]);
+    const uint32_t lo = (uint32_t)bits, hi = (uint32_t)(bits >> 32);
+    for (int p = 0; p < world; ++p) {
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(peers[p]) + ll) + ((size_t)rank * 2 + slot) * cap + i;
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(tag), "r"(hi), "r"(tag) : "memory");
+    }
+  }
+  // 2. gather: element i of every rank from my own inbox, in rank order
+  const uint4* inbox = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(peers[rank]) + ll) + (size_t)slot * cap;
+  const long long t0 = clock64();
+  for (int i = threadIdx.x; i < n; i += kXchgThreads) {
+    double s = 0.0;
+    for (int p = 0; p < world; ++p) {
+      const uint4* src = inbox + (size_t)p * 2 * cap + i;
+      uint32_t a, ta, b, tb;
+      for (unsigned it = 1;; ++it) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(ta), "=r"(b), "=r"(tb) : "l"(src) : "memory");
+        if (ta == tag && tb == tag) break;
+        // a tag from the future: this rank's peers have moved on by two exchanges -- the call sequences diverged
+        if ((int32_t)(ta - tag) > 0 && (int32_t)(tb - tag) > 0) { failed = 2; break; }
+        if ((it & 0xffffu) == 0) {
+          if (*reinterpret_cast<volatile int*>(&failed) != 0) break;               // another thread of this CTA gave up
+          if (*reinterpret_cast<volatile int*>(err) != 0) { failed = 1; break; }   // an earlier exchange already failed
+          if (clock64() - t0 > 240000000000ll) { failed = 1; break; }              // ~2 min: the peer is gone
+        }
+      }
+      if (*reinterpret_cast<volatile int*>(&failed) != 0) break;
+      s += __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+    }
+    buf[i] = s;
+  }
+  __syncthreads();
+  if (failed) {
+    if (threadIdx.x == 0) { *reinterpret_cast<volatile int*>(err) = failed; __threadfence_system(); }
+    for (int i = threadIdx.x; i < n; i += kXchgThreads) buf[i] = __longlong_as_double(0x7ff8000000000000ll);
+  }
+}
+
 int dp_allreduce_doubles(DpState* dp, double* buf, size_t n, cudaStream_t st) {
   if (dp->xchg_ready && (int)n <= dp->xchg_cap) {
     const unsigned long long seq = ++dp->xchg_seq;
+    static int use_ll = -1;
+    if (use_ll < 0) {
+      const char* e = getenv("RNVP_XCHG_LL");           // A/B switch: 0 = the fenced data + flag protocol
+      use_ll = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (use_ll) {
+      stats_exchange_ll_kernel<<<1, kXchgThreads, 0, st>>>(dp->xchg_peers_dev, dp->rank, dp->world, dp->xchg_cap, buf, (int)n,
+                                                           seq, dp->xchg_err);
+      RNVP_LAUNCH_CHECK();
+      return RNVP_OK;
+    }
     // plain launch: programmatic dependent launch bought nothing here (measured) and the exchange is the one
     // kernel whose early start could only add waiting peers
     stats_exchange_kernel<<<1, kXchgThreads, 0, st>>>(dp->xchg_peers_dev, dp->rank, dp->world, dp->xchg_cap, buf, (int)n,
@@ -268,7 +341,9 @@ int rnvp_dp_xchg_alloc(rnvp_plan* plan, int cap_doubles, void* ipc_handle64) {
   RNVP_REQUIRE(dp->xchg_local == nullptr, "statistic exchange already allocated");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
   // [world][2][cap] doubles, [world] peer sequence flags, 1 local "arrived" word (fused exchange, common.cuh)
-  const size_t bytes = (size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)(dp->world + 1) * sizeof(unsigned long long);
+  // ... then the LL inbox [world][2][cap] x 16 bytes (stats_exchange_ll_kernel)
+  const size_t bytes = ((((size_t)dp->world * 2 * cap_doubles * sizeof(double) + (size_t)(dp->world + 1) * sizeof(unsigned long long)) + 15) &
+                        ~(size_t)15) + (size_t)dp->world * 2 * cap_doubles * 16;
   RNVP_CUDA(cudaMalloc(&dp->xchg_local, bytes));
   RNVP_CUDA(cudaMemset(dp->xchg_local, 0, bytes));
   RNVP_CUDA(cudaHostAlloc(&dp->xchg_err_host, sizeof(int), cudaHostAllocMapped));

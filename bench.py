@@ -570,9 +570,12 @@ def run_b200(args):
                                                fused_reduce=args.math == "tf32")
             r["alg_bytes"], r["alg_flops"] = byt, fl
             r["kernel"] = kernel_name_of(r["kind"], r["taps"], r["cin"], r["cout"], args.math, xform_on)
-            gsum = groups.setdefault(r["kernel"], dict(ms=0.0, launches=0, bytes=0.0, flops=0.0))
+            gsum = groups.setdefault(r["kernel"], dict(ms=0.0, launches=0, bytes=0.0, flops=0.0, roof_ms=0.0))
             gsum["ms"] += r["ms"]; gsum["launches"] += r["launches"]
             gsum["bytes"] += byt * r["launches"]; gsum["flops"] += fl * r["launches"]
+            # time this class would take at ITS OWN binding roof (a kernel name covers HBM-bound and tensor-bound shapes)
+            gsum["roof_ms"] += r["launches"] * 1e3 * max(byt / (peaks["hbm_gbs"] * 1e9),
+                                                         fl / (peaks["bf16_tflops"] * 0.5 * 1e12))
         if groups:
             # the dominant kernel = the CUDA kernel (ncu name) with the largest share of the profiled kernel time;
             # achieved = its algorithmic bytes (flops) per launch / its average launch duration, over all its launches
@@ -600,6 +603,9 @@ def run_b200(args):
             roof["algorithmic_flops_per_launch"] = fl
             roof["hbm_frac_of_this_kernel"] = gbs / peaks["hbm_gbs"]
             roof["tensor_frac_of_this_kernel"] = tfs / tf32_peak
+            # the same kernel with every launch class held against its own binding roof (HBM for the S >= 16 shapes,
+            # the TF32 tensor roof for the 3x3 / deep ones): sum of roofline times / sum of measured times
+            roof["frac_vs_own_roof_per_class"] = gk["roof_ms"] / gk["ms"]
             try:                                          # DRAM bytes per launch from the committed ncu capture
                 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
                     roof["traffic"] = json.load(f).get(kname)
@@ -608,7 +614,8 @@ def run_b200(args):
             roof["by_kernel"] = {k: {"share": v["ms"] / tot, "launches_per_step": v["launches"] // nprof,
                                      "avg_us": v["ms"] / v["launches"] * 1e3,
                                      "hbm_frac": v["bytes"] / (v["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"],
-                                     "tensor_frac": v["flops"] / (v["ms"] / 1e3) / 1e12 / tf32_peak}
+                                     "tensor_frac": v["flops"] / (v["ms"] / 1e3) / 1e12 / tf32_peak,
+                                     "frac_vs_own_roof_per_class": v["roof_ms"] / v["ms"]}
                                  for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
             # whole-step roofline on SURVEY.md 8(d) algorithmic bytes: conv activations in + out once each
             # (41.436 M elements per image and pass, fp32 storage), training = 2.5 passes

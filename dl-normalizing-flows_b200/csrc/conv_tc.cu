@@ -1216,9 +1216,23 @@ __device__ __forceinline__ void tmem_dealloc_dyn(uint32_t taddr, uint32_t ncols)
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmDy,
-                                                                     const __grid_constant__ CUtensorMap tmX,
-                                                                     const WgradTcParams prm) {
+// J > 1: a GROUP of J independent weight gradients of one shape in one launch (blockIdx.z = job): the 2R 1x1 and the
+// R 3x3 wgrads of a coupling's residual blocks.  At the deep scales a launch has 2-6 us of work under an 8 us launch
+// floor, and whatever runs there runs alone (every kernel fills the SMs' shared memory), so launches saved are time saved.
+template <int J> struct WgOperands {
+  CUtensorMap m[2 * J];                     // (dy, x) maps of job j at [2j], [2j + 1]
+  float* dw[J];
+  float* dbias[J];
+  const float* xf_save[J];
+};
+template <int J>
+__global__ void __launch_bounds__(TC_THREADS) conv_wgrad_tf32_kernel(const __grid_constant__ WgOperands<J> ops,
+                                                                     const WgradTcParams prm_in) {
+  const int job = J > 1 ? (int)blockIdx.z : 0;
+  const CUtensorMap& tmDy = ops.m[2 * job];
+  const CUtensorMap& tmX = ops.m[2 * job + 1];
+  WgradTcParams prm = prm_in;
+  prm.dw = ops.dw[job]; prm.dbias = ops.dbias[job]; prm.xf_save = ops.xf_save[job];
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int WG_A_STAGES = prm.a_stages, WG_B_STAGES = prm.b_stages;
@@ -1537,19 +1551,27 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
     return k_conv_wgrad_fp32(a, st);
   }
   RNVP_REQUIRE(a.taps == 1 || a.taps == 9, "wgrad: taps=%d", a.taps);
-  CUtensorMap tmDy, tmX;
+  const int njobs = a.njobs > 1 ? a.njobs : 1;
+  RNVP_REQUIRE(njobs <= kMaxWgradJobs && (njobs == 1 || (a.jobs != nullptr && a.segs == 1)),
+               "wgrad: a group holds at most %d jobs of one shape, no K-concatenated x", kMaxWgradJobs);
+  WgOperands<kMaxWgradJobs> ops{};
   // MN-major fp32 operands: 128B swizzle with 32-byte atoms (the only layout tcgen05 accepts for them)
-  RNVP_TRY(make_act_map(&tmDy, a.dy, a.B, a.S, a.lddy, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-  RNVP_TRY(make_act_map(&tmX, a.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, a.segs, a.seg_stride));
+  for (int j = 0; j < njobs; ++j) {
+    const WgradJob one{a.x, a.dy, a.dw, a.dbias, a.xf_save};
+    const WgradJob& jb = njobs > 1 ? a.jobs[j] : one;
+    RNVP_TRY(make_act_map(&ops.m[2 * j], jb.dy, a.B, a.S, a.lddy, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+    RNVP_TRY(make_act_map(&ops.m[2 * j + 1], jb.x, a.B, a.S, a.kpad, bw, bh, bn, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, a.segs,
+                          a.seg_stride));
+    ops.dw[j] = jb.dw; ops.dbias[j] = jb.dbias; ops.xf_save[j] = jb.xf_save;
+  }
   RNVP_REQUIRE(a.segs >= 1 && (a.segs == 1 || (a.xf_save == nullptr && a.seg_stride % 4 == 0)),
                "wgrad: K-concatenated x needs 16-byte aligned segments and excludes the BN prologue");
   const int ktot = a.segs * a.kpad;
   WgradTcParams prm{};
-  prm.dw = a.dw; prm.dbias = a.dbias;
   prm.P = P; prm.n = a.n; prm.npad = a.npad; prm.kpad = ktot; prm.taps = a.taps; prm.S = a.S;
   prm.seg_k = a.kpad; prm.lddw = a.lddw ? a.lddw : ktot;
   prm.x3 = a.x3;
-  prm.xf_save = a.xf_save; prm.xf_C = a.xf_C;
+  prm.xf_C = a.xf_C;
   prm.log2S = 0;
   while ((1 << prm.log2S) < a.S) ++prm.log2S;
   prm.n_tiles = ceil_div(a.n, 128);
@@ -1571,7 +1593,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
   prm.num_tiles = ceil_div(P, 64);
   const int base = prm.n_tiles * prm.k_tiles * prm.tap_ranges;
   // pixel splits: fill the resident slots in ONE wave (rounding up would leave a second, nearly empty wave)
-  int splits = kNumSMs / base < 1 ? 1 : kNumSMs / base;
+  int splits = kNumSMs / (base * njobs) < 1 ? 1 : kNumSMs / (base * njobs);
   if (splits > prm.num_tiles) splits = prm.num_tiles;
   prm.tiles_per_split = ceil_div(prm.num_tiles, splits);
   splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
@@ -1614,7 +1636,7 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
     // BN prologue: the transform is one more pipeline step; RNVP_WG_XF_DEEP=1 trades the second CTA per SM for a
     // four-deep A ring on those launches (A/B switch)
     static const int xf_deep = env_int("RNVP_WG_XF_DEEP", 0, 1, 0);
-    if (variant != 0 && !(a.xf_save && xf_deep) && prm.tmem_cols <= 256 &&
+    if (variant != 0 && !(ops.xf_save[0] && xf_deep) && prm.tmem_cols <= 256 &&
         2 * prm.a_stage_bytes + 2 * prm.b_stage_bytes <= 100 * 1024) {
       prm.a_stages = 2;                             // two CTAs per SM hide the per-tile latency better
       prm.b_stages = (100 * 1024 - 2 * prm.a_stage_bytes) / prm.b_stage_bytes;
@@ -1628,20 +1650,29 @@ int k_conv_wgrad_tf32(const WgradArgs& a, cudaStream_t st) {
     prm.ring_bytes = prm.a_stages * prm.a_stage_bytes + prm.b_stages * prm.b_stage_bytes;
   }
   prm.ring_bytes = (prm.ring_bytes + 1023) / 1024 * 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RNVP_CUDA(cudaFuncSetAttribute(conv_wgrad_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
-    attr_set = true;
-  }
+  static const bool attr_set = [] {              // thread-safe first call (autograd's backward thread may be first)
+    return cudaFuncSetAttribute(conv_wgrad_tf32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) == cudaSuccess &&
+           cudaFuncSetAttribute(conv_wgrad_tf32_kernel<kMaxWgradJobs>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) ==
+               cudaSuccess;
+  }();
+  RNVP_REQUIRE(attr_set, "wgrad: cudaFuncSetAttribute failed");
   // with the compact layout two CTAs fit per SM: split the pixel range accordingly
   const int dyn_smem = prm.ring_bytes + 1024;
   if (two_ctas && 2 * (dyn_smem + 2048) <= 227 * 1024 && prm.tmem_cols <= 256) {
-    int splits2 = 2 * kNumSMs / base < 1 ? 1 : 2 * kNumSMs / base;
+    int splits2 = 2 * kNumSMs / (base * njobs) < 1 ? 1 : 2 * kNumSMs / (base * njobs);
     if (splits2 > prm.num_tiles) splits2 = prm.num_tiles;
     prm.tiles_per_split = ceil_div(prm.num_tiles, splits2);
     splits = ceil_div(prm.num_tiles, prm.tiles_per_split);
   }
-  RNVP_CUDA(launch_pdl(conv_wgrad_tf32_kernel, dim3(base, splits), dim3(TC_THREADS), (size_t)dyn_smem, st, tmDy, tmX, prm));
+  if (njobs > 1) {
+    RNVP_CUDA(launch_pdl(conv_wgrad_tf32_kernel<kMaxWgradJobs>, dim3(base, splits, njobs), dim3(TC_THREADS), (size_t)dyn_smem, st,
+                         ops, prm));
+  } else {
+    WgOperands<1> one{};
+    one.m[0] = ops.m[0]; one.m[1] = ops.m[1];
+    one.dw[0] = ops.dw[0]; one.dbias[0] = ops.dbias[0]; one.xf_save[0] = ops.xf_save[0];
+    RNVP_CUDA(launch_pdl(conv_wgrad_tf32_kernel<1>, dim3(base, splits), dim3(TC_THREADS), (size_t)dyn_smem, st, one, prm));
+  }
   RNVP_LAUNCH_CHECK();
   return RNVP_OK;
 }

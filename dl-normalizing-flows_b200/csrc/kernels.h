@@ -235,6 +235,15 @@ int k_conv_fwd_fp32(const ConvArgs& a, cudaStream_t st);
 int k_conv_fwd_tf32(const ConvArgs& a, cudaStream_t st);
 bool conv_tf32_fusable(const ConvArgs& a);   // true when k_conv_fwd_tf32 runs the tensor-core kernel for `a`
 bool conv_tf32_prologue_ok(const ConvArgs& a);   // ... and can take a BnPrologue
+// one member of a wgrad group (k_conv_wgrad_tf32 with njobs > 1): jobs share the shape, every pointer is per job
+constexpr int kMaxWgradJobs = 8;
+struct WgradJob {
+  const float* x;
+  const float* dy;
+  float* dw;
+  float* dbias;          // or null
+  const float* xf_save;  // or null
+};
 struct WgradArgs {
   const float* x;      // [B,S,S,kpad]
   const float* dy;     // [P,lddy]
@@ -250,6 +259,10 @@ struct WgradArgs {
   size_t seg_stride = 0;
   int lddw = 0;
   int x3 = 0;          // 3xTF32: x and dy boxes are split into hi / lo in shared memory, three MMAs per K step
+  // tensor-core kernel only: njobs > 1 = a group of independent wgrads of this shape in ONE launch; x / dy / dw / dbias /
+  // xf_save above are then ignored in favour of jobs[0 .. njobs)
+  int njobs = 1;
+  const WgradJob* jobs = nullptr;
 };
 bool wgrad_tf32_prologue_ok(const WgradArgs& a);
 int k_conv_wgrad_fp32(const WgradArgs& a, cudaStream_t st);

@@ -761,6 +761,18 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     RNVP_TRY(wgrad_bn(oc, 3 * R, c.act(ci, A.skip), dst, d.cst_pad, gbias(oc)));
     RNVP_TRY(dgrad_bn_bwd(oc, dst, 3 * R, G0, c.act(ci, A.skip), DO, nullptr, true));
   }
+  // Grouped weight gradients (tensor-core tiers, workspace mode 2 where every dy has its own buffer): the 2R 1x1 wgrads
+  // (rb0, rb6 of every block) and the R 3x3 wgrads (rb3) of the coupling are collected here and issued as ONE launch
+  // each after the dgrad chain -- 3R - 2 launches fewer per coupling.  RNVP_WGRAD_GROUPED=0 restores one launch per conv.
+  static const bool grouped_on = [] { const char* e = getenv("RNVP_WGRAD_GROUPED"); return !(e && e[0] == '0'); }();
+  bool grouped = grouped_on && fresh && tc_tier(p) && A.keep_h && 2 * R <= kMaxWgradJobs;
+  for (int i = 0; i < R && grouped; ++i) grouped = bn_fused(p, d, 3 * i) && bn_fused(p, d, 3 * i + 2) && !bn_fused(p, d, 3 * i + 1);
+  {
+    WgradArgs w{};
+    w.S = S; w.kpad = ld; w.lddy = ld;
+    grouped = grouped && wgrad_tf32_prologue_ok(w);
+  }
+  std::vector<WgradJob> jobs1, jobs3;
   const bool sfused = skip_fused(p, d, c.B, c.mode);
   if (sfused) {
     // all R+1 skip wgrads in one launch: dw[n][(i, k)] = sum_p DO[p,n] * a_i[p,k]; the bias gradient (the same column
@@ -786,20 +798,39 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
     // a_{i+1} = a_i + rb6(relu(bn3(u2)))
     float* G3 = take(1);
     RNVP_TRY(recompute(3 * i + 2, u2));
-    RNVP_TRY(wgrad_bn(*rb6, 3 * i + 2, u2, DAc, ld, gbias(*rb6)));
+    if (grouped) jobs1.push_back(WgradJob{u2, DAc, c.dw() + rb6->dw_off, gbias(*rb6), c.save(d.bns[3 * i + 2].save)});
+    else RNVP_TRY(wgrad_bn(*rb6, 3 * i + 2, u2, DAc, ld, gbias(*rb6)));
     RNVP_TRY(dgrad_bn_bwd(*rb6, DAc, 3 * i + 2, G3, u2, G3, nullptr, true));
     // u2 = rb3(relu(bn2(u1)))
     float* G2 = take(2);
     RNVP_TRY(recompute(3 * i + 1, u1));
-    RNVP_TRY(wgrad_bn(*rb3, 3 * i + 1, u1, G3, ld, nullptr));
+    if (grouped) jobs3.push_back(WgradJob{H, G3, c.dw() + rb3->dw_off, nullptr, nullptr});     // H = kept relu(bn2(u1))
+    else RNVP_TRY(wgrad_bn(*rb3, 3 * i + 1, u1, G3, ld, nullptr));
     RNVP_TRY(dgrad_bn_bwd(*rb3, G3, 3 * i + 1, G2, u1, G2, nullptr, true));
     // u1 = rb0(relu(bn1(a_i)))
     float* G1 = take(1);
     float* DAn = take(3);
     RNVP_TRY(recompute(3 * i, ai));
-    RNVP_TRY(wgrad_bn(*rb0, 3 * i, ai, G2, ld, nullptr));
+    if (grouped) jobs1.push_back(WgradJob{ai, G2, c.dw() + rb0->dw_off, nullptr, c.save(d.bns[3 * i].save)});
+    else RNVP_TRY(wgrad_bn(*rb0, 3 * i, ai, G2, ld, nullptr));
     RNVP_TRY(dgrad_bn_bwd(*rb0, G2, 3 * i, G1, ai, DAn, DAc, false));
     DA = DAn;
+  }
+  if (grouped) {
+    RNVP_TRY(fork_to_side(c));               // every dy of the coupling's residual blocks has been produced
+    const ConvDesc& r0 = cv[2], &r3 = cv[3];
+    auto launch_group = [&](const std::vector<WgradJob>& jobs, const ConvDesc& cvw, bool xf) -> int {
+      ProfScope ps(PROF_WGRAD, S, cvw.taps, (int)jobs.size() * cvw.cin, cvw.cout, c.wst);
+      WgradArgs a{};
+      a.B = c.B; a.S = S; a.kpad = cvw.kpad; a.n = cvw.cout; a.npad = cvw.npad; a.taps = cvw.taps; a.lddy = ld;
+      a.lddw = cvw.ld_dw; a.x3 = x3_tier(p);
+      a.xf_C = xf ? d.D : 0;
+      a.njobs = (int)jobs.size(); a.jobs = jobs.data();
+      if (a.njobs == 1) { a.x = jobs[0].x; a.dy = jobs[0].dy; a.dw = jobs[0].dw; a.dbias = jobs[0].dbias; a.xf_save = jobs[0].xf_save; }
+      return k_conv_wgrad_tf32(a, c.wst);
+    };
+    RNVP_TRY(launch_group(jobs1, r0, true));
+    RNVP_TRY(launch_group(jobs3, r3, false));
   }
   // skip = in_skip(a0) (+...); a0 = in_block(h0)
   float* DAf = take(3);

@@ -764,8 +764,11 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   // Grouped weight gradients (tensor-core tiers, workspace mode 2 where every dy has its own buffer): the 2R 1x1 wgrads
   // (rb0, rb6 of every block) and the R 3x3 wgrads (rb3) of the coupling are collected here and issued as ONE launch
   // each after the dgrad chain -- 3R - 2 launches fewer per coupling.  RNVP_WGRAD_GROUPED=0 restores one launch per conv.
+  // Single process only: under data parallelism the grouped launches measured SLOWER (2 GPUs, same session: 73.1 - 73.4
+  // vs 72.2 ms per step) -- one long low-priority kernel holds the SMs while the main stream's statistic exchanges and
+  // their small consumers queue behind it, and every such delay is a wait for all ranks at the next exchange.
   static const bool grouped_on = [] { const char* e = getenv("RNVP_WGRAD_GROUPED"); return !(e && e[0] == '0'); }();
-  bool grouped = grouped_on && fresh && tc_tier(p) && A.keep_h && 2 * R <= kMaxWgradJobs;
+  bool grouped = grouped_on && p->world == 1 && fresh && tc_tier(p) && A.keep_h && 2 * R <= kMaxWgradJobs;
   for (int i = 0; i < R && grouped; ++i) grouped = bn_fused(p, d, 3 * i) && bn_fused(p, d, 3 * i + 2) && !bn_fused(p, d, 3 * i + 1);
   {
     WgradArgs w{};

@@ -1,4 +1,5 @@
-// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, TF32 operands, fp32 accumulate.
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a, fp32 accumulate, two operand tiers: TF32 (kind::tf32
+// on fp32 words that their producers rounded to TF32) and 3xTF32 (split operands, the fp32-accurate tier, "X3" below).
 //
 //   forward / dgrad :  y[p,n] = sum_tap sum_k x[p+tap,k] * w[tap][n][k]  (+bias) (+res)  [+ BN stats]
 //   wgrad           :  dw[tap][n][k] += sum_p dy[p,n] * x[p+tap,k]       (+ dbias[n] += sum_p dy[p,n])
@@ -7,21 +8,22 @@
 // and are read by the tensor core as TF32 (kind::tf32), so no conversion pass exists.
 //
 // forward: CTA tile = 128 output pixels x BN channels.  The A tile of one (tap, 32-channel chunk)
-// is ONE 4-D TMA box (32 ch, bw, bh, bn) with bw*bh*bn = 128 whose W/H coordinates are shifted by
+// is ONE 5-D TMA box (32 ch, bw, bh, bn, 1 tensor) with bw*bh*bn = 128 whose W/H coordinates are shifted by
 // the tap: out-of-image pixels are zero-filled by TMA, so the 3x3 halo costs no instructions and no
-// im2col buffer.  B is a 3-D box over w[tap][n][k].  Both land in 128B-swizzled, K-major smem and
+// im2col buffer; the fifth coordinate walks the tensors of a K-concatenated input (the fused skip path).
+// B is a 3-D box over w[tap][n][k].  Both land in 128B-swizzled, K-major smem and
 // feed tcgen05.mma (M=128, N=BN, K=8) x4 per chunk; the accumulator lives in TMEM, double buffered.
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+TMEM alloc), then 4 (BN <= 64, two CTAs per
 // SM) or 8 (BN = 128, one CTA per SM) epilogue warps: tcgen05.ld, bias, residual (TMA-prefetched box),
 // TMA store from a swizzled staging box, per-channel sum / sum-of-squares for the next batch norm read
-// back from that box -- or, as a dgrad, the ReLU mask and the two BN-backward sums.
-// An opt-in "halo" mode loads one haloed tile per chunk and feeds all nine taps through row-shifted
-// descriptors (correct, not faster: see halo_enabled()).
+// back from that box -- or, as a dgrad, the ReLU mask and the two BN-backward sums -- and, in the XF
+// instantiations, four transform warps that rewrite the landed A tiles (BN + ReLU prologue, 3xTF32 split).
 //
 // wgrad: both operands are MN-major views of the same kind of TMA tiles (pixels are the GEMM K
 // dimension): A = tap-shifted x tiles (M = (tap, in channel)), B = dy tile (N = out channels); one CTA
 // owns a (n-tile, k-tile, tap-group, pixel-range) slab, keeps up to 512 TMEM columns of partial dw
-// and flushes them with fp32 atomics; the bias gradient comes from the staged dy boxes.
+// and flushes them with fp32 atomics; the bias gradient comes from the staged dy boxes.  A launch may carry a
+// group of up to 8 independent wgrads of one shape (blockIdx.z).
 #include <cuda.h>
 #include <cstdlib>
 #include "kernels.h"

@@ -768,7 +768,9 @@ int net_backward(const Ctx& c, int ci, const float* dst, float* dh0) {
   // vs 72.2 ms per step) -- one long low-priority kernel holds the SMs while the main stream's statistic exchanges and
   // their small consumers queue behind it, and every such delay is a wait for all ranks at the next exchange.
   static const bool grouped_on = [] { const char* e = getenv("RNVP_WGRAD_GROUPED"); return !(e && e[0] == '0'); }();
-  bool grouped = grouped_on && p->world == 1 && fresh && tc_tier(p) && A.keep_h && 2 * R <= kMaxWgradJobs;
+  // TF32 tier only: the 3xTF32 wgrad runs one CTA per SM on a shallow ring, and fewer pixel splits per job cost it
+  // more than the launches save (measured 136.9 vs 129.2 ms per step).
+  bool grouped = grouped_on && p->world == 1 && p->math == RNVP_MATH_TF32 && fresh && A.keep_h && 2 * R <= kMaxWgradJobs;
   for (int i = 0; i < R && grouped; ++i) grouped = bn_fused(p, d, 3 * i) && bn_fused(p, d, 3 * i + 2) && !bn_fused(p, d, 3 * i + 1);
   {
     WgradArgs w{};

@@ -57,6 +57,31 @@ def test_plan_table_matches_state_dict(pkg):
         cabi.lib.rnvp_plan_destroy(h)
 
 
+def test_math_tiers_and_workspace_sizes(pkg):
+    """Host arithmetic of the three arithmetic tiers: the 3xTF32 tier keeps a lo copy of every weight layout (the
+    weight arena doubles), workspace mode 2 (keeps activations) is larger than the lean mode 1, and an unknown tier
+    is rejected."""
+    cabi = pkg.rnvp_cabi
+    assert cabi.MATH_BY_NAME == {"fp32": 0, "tf32": 1, "tf32x3": 2}
+    cfg = cabi.Config(3, 64, 32, 4, 5, 0.0, 1.0)
+    h = C.c_void_p()
+    cabi.check(cabi.lib.rnvp_plan_create(C.byref(cfg), C.byref(h)))
+    try:
+        size = {}
+        for name, mode in cabi.MATH_BY_NAME.items():
+            cabi.check(cabi.lib.rnvp_plan_set_math(h, mode))
+            size[name] = [cabi.lib.rnvp_plan_workspace_bytes(h, 8, m) for m in (0, 1, 2)]
+            assert 0 < size[name][0] < size[name][1] <= size[name][2], (name, size[name])
+        # 120.15 M parameters -> two padded layouts of every conv (forward + dgrad operand) ~ 1 GB of fp32 weights;
+        # the lo copy of the 3xTF32 tier adds the same amount again, in every workspace mode
+        extra = [a - b for a, b in zip(size["tf32x3"], size["tf32"])]
+        assert all(0.9e9 < e < 1.2e9 for e in extra), extra
+        assert cabi.lib.rnvp_plan_set_math(h, 7) != 0
+        assert b"math" in cabi.lib.rnvp_last_error()
+    finally:
+        cabi.lib.rnvp_plan_destroy(h)
+
+
 def test_plan_rejects_bad_config(pkg):
     cabi = pkg.rnvp_cabi
     h = C.c_void_p()

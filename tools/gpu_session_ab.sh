@@ -39,6 +39,8 @@ for s in "$@"; do
     targets) TIME=1 timeout 300 python tools/ncu_targets.py > $OUT/${TAG}_targets.log 2>&1 ;;
     ncu_targets) timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_(fwd|wgrad)_tf32" -c 27 \
                    -o $OUT/${TAG}_targets python tools/ncu_targets.py > $OUT/${TAG}_ncu_targets.log 2>&1 ;;
+    sampleenv:*) name=$(echo $s | cut -d: -f2); envs=$(echo $s | cut -d: -f3 | tr ',' ' ')
+      env $envs timeout 600 python bench.py --mode sample --batch 4096 --steps 5 --warmup 3 --no-cpu-baseline --no-gpu-eager --no-prof > $OUT/${TAG}_sample_${name}.json 2> $OUT/${TAG}_sample_${name}.err ;;
     smoke) timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
